@@ -66,7 +66,8 @@ def test_oracle_matches_reference_golden(path):
     kw = {k: (None if z[k].dtype == object and z[k].item() is None else z[k]) for k in z["scene_keys"]}
     sc = util.random_scene(**{k: (v.item() if hasattr(v, "item") and np.ndim(v) == 0 else v) for k, v in kw.items()})
     g = (z["g_color"], z["g_depth"], z["g_alpha"])
-    out = util.run_oracle(sc, g)
+    # backward starts from the reference's own forward alpha (see RasterOracle.backward)
+    out = util.run_oracle(sc, g, alpha_from=z["alpha"])
     assert np.array_equal(out["radii"], z["radii"])
     assert out["R"] == int(z["num_rendered"])
     util.assert_close("color", out["color"], z["color"])

@@ -1,0 +1,152 @@
+"""Parity tests proper (-m gpu): the product's CUDA path, called through the C ABI behind the
+reference-shaped Python surface, against
+  (1) the UNMODIFIED reference CUDA kernels built into oracle/_ref (the pin), and
+  (2) the CPU oracle (oracle/raster_oracle.c) at sizes it finishes in seconds.
+Tolerance: 1e-4 relative max-norm per tensor (BASELINE.json north_star), radii bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+from tests import raster_harness as Hn
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # name: kwargs of util.random_scene
+    "small": dict(P=500, W=64, H=48, seed=101),
+    "ragged": dict(P=2000, W=97, H=75, seed=102),               # image not a multiple of the 16x16 tile
+    "dense": dict(P=6000, W=128, H=128, seed=103, spread=0.5),   # long per-tile lists, early termination
+    "translucent": dict(P=3000, W=96, H=96, seed=104, opacity_mean=-3.0),
+    "sh3": dict(P=1500, W=80, H=64, seed=105, sh_degree=3),
+    "sh1": dict(P=700, W=48, H=64, seed=106, sh_degree=1),
+    "sh0": dict(P=700, W=48, H=64, seed=107, sh_degree=0),
+    "cov_precomp": dict(P=1500, W=80, H=80, seed=108, cov_precomp=True),
+    "all_behind": dict(P=300, W=40, H=40, seed=109, behind_frac=1.0),
+    "one": dict(P=1, W=33, H=17, seed=110, behind_frac=0.0, big_frac=1.0),
+    "wide_image": dict(P=4000, W=640, H=64, seed=111, spread=1.5),
+}
+
+
+@pytest.fixture(scope="module")
+def ref_available():
+    from oracle import ref_rasterizer
+    if not ref_rasterizer.available():
+        pytest.fail("oracle/_ref/libref_rasterizer.so missing: run `python oracle/build_ref.py` where /root/reference exists")
+    return True
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_product_matches_reference_kernels(name, built_lib, ref_available):
+    sc = util.random_scene(**CASES[name])
+    g = util.upstream_grads(sc["W"], sc["H"], CASES[name]["seed"])
+    want = Hn.run_reference(sc, g)
+    got = Hn.run_product(sc, g)
+    rep = Hn.compare(name, got, want, util.TOL, util.assert_close)
+    print(name, {k: "%.1e" % v for k, v in rep.items()})
+
+
+@pytest.mark.parametrize("name", ["small", "ragged", "sh3", "cov_precomp", "translucent"])
+def test_product_matches_cpu_oracle(name, built_lib):
+    sc = util.random_scene(**CASES[name])
+    g = util.upstream_grads(sc["W"], sc["H"], CASES[name]["seed"])
+    got = Hn.run_product(sc, g)
+    want = util.run_oracle(sc, g, alpha_from=got["alpha"])  # same T_final = 1 - alpha on both sides
+    Hn.compare(name, got, want, util.TOL, util.assert_close)
+
+
+@pytest.mark.parametrize("name", ["small", "dense", "sh3", "cov_precomp"])
+def test_oracle_pinned_by_reference_kernels(name, ref_available):
+    """The oracle is only trustworthy if it agrees with the real reference."""
+    sc = util.random_scene(**CASES[name])
+    g = util.upstream_grads(sc["W"], sc["H"], CASES[name]["seed"])
+    want = Hn.run_reference(sc, g)
+    got = util.run_oracle(sc, g, alpha_from=want["alpha"])
+    assert got["R"] == want["R"]
+    Hn.compare(name, got, want, util.TOL, util.assert_close)
+
+
+def test_empty_input(built_lib):
+    sc = util.random_scene(0, 50, 30, seed=5)
+    got = Hn.run_product(sc)
+    for c in range(3):
+        assert np.allclose(got["color"][c], sc["bg"][c])
+    assert not got["alpha"].any() and not got["depth"].any()
+
+
+def test_argument_errors(built_lib):
+    from animatablegaussians_b200 import rasterizer as R
+    sc = util.random_scene(10, 32, 32, seed=6)
+    rast = R.GaussianRasterizer(Hn.settings_for(sc))
+    m = Hn.to_dev(sc["xyz"])
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rast(means3D=m, means2D=m, opacities=Hn.to_dev(sc["opacity"]), scales=Hn.to_dev(sc["scales"]),
+             rotations=Hn.to_dev(sc["rotations"]))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+        rast(means3D=m, means2D=m, opacities=Hn.to_dev(sc["opacity"]), colors_precomp=Hn.to_dev(sc["rgb"]))
+    with pytest.raises(RuntimeError, match="means3D must have dimensions"):
+        rast(means3D=m[:, :2], means2D=m, opacities=Hn.to_dev(sc["opacity"]), colors_precomp=Hn.to_dev(sc["rgb"]),
+             scales=Hn.to_dev(sc["scales"]), rotations=Hn.to_dev(sc["rotations"]))
+
+
+def test_mark_visible_matches_reference(built_lib, ref_available):
+    from animatablegaussians_b200 import rasterizer as R
+    from oracle.ref_rasterizer import RefRasterizer
+    from oracle import raster_oracle
+    sc = util.random_scene(5000, 64, 64, seed=7, behind_frac=0.4)
+    rast = R.GaussianRasterizer(Hn.settings_for(sc))
+    got = rast.markVisible(Hn.to_dev(sc["xyz"])).cpu().numpy()
+    want = RefRasterizer().mark_visible(Hn.to_dev(sc["xyz"]), Hn.to_dev(sc["viewmatrix"]), Hn.to_dev(sc["projmatrix"]))
+    torch.cuda.synchronize()
+    assert np.array_equal(got, want.cpu().numpy())
+    assert np.array_equal(got, raster_oracle.mark_visible(sc["xyz"], sc["viewmatrix"], sc["projmatrix"]))
+
+
+def test_view_batch_equals_per_view_calls(built_lib):
+    """V views in one call == V single-view calls (outputs identical, shared-parameter gradients summed)."""
+    from animatablegaussians_b200 import rasterizer as R, synthetic as S, camera as C
+    P, V, img = 20000, 4, 256
+    g = S.make_gaussians(P, seed=3)
+    extrs, Ks = S.ring_cameras(V, img=img, focal=275.0)
+    dev = "cuda"
+    leaf = lambda a: torch.from_numpy(a).to(dev).requires_grad_(True)
+    rng = np.random.default_rng(0)
+    rgbv = rng.uniform(0, 1, (V, P, 3)).astype(np.float32)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    up = [torch.from_numpy(rng.normal(0, 1, s).astype(np.float32)).to(dev) for s in ((V, 3, img, img), (V, 1, img, img), (V, 1, img, img))]
+
+    x, o, s, q, c = leaf(g["xyz"]), leaf(g["opacity"]), leaf(g["scales"]), leaf(g["rotations"]), leaf(rgbv)
+    bs = C.make_batched_settings(extrs, Ks, img, img, bg, dev)
+    color, radii, depth, alpha = R.rasterize_gaussians_batched(x, None, None, c, o, s, q, None, bs)
+    torch.autograd.backward([color, depth, alpha], up)
+    gb = [t.grad.clone() for t in (x, o, s, q, c)]
+
+    x2, o2, s2, q2, c2 = leaf(g["xyz"]), leaf(g["opacity"]), leaf(g["scales"]), leaf(g["rotations"]), leaf(rgbv)
+    outs = []
+    for v in range(V):
+        rs = C.make_raster_settings(extrs[v], Ks[v], img, img, bg, dev)
+        outs.append(R.GaussianRasterizer(rs)(means3D=x2, means2D=torch.zeros_like(x2), opacities=o2, colors_precomp=c2[v],
+                                             scales=s2, rotations=q2))
+    col1 = torch.stack([o_[0] for o_ in outs]); dep1 = torch.stack([o_[2] for o_ in outs]); alp1 = torch.stack([o_[3] for o_ in outs])
+    torch.autograd.backward([col1, dep1, alp1], up)
+    assert torch.equal(radii, torch.stack([o_[1] for o_ in outs]))
+    assert torch.equal(color, col1) and torch.equal(depth, dep1) and torch.equal(alpha, alp1)
+    for name, a, b in zip(("xyz", "opacity", "scales", "rot", "colors"), gb, (x2.grad, o2.grad, s2.grad, q2.grad, c2.grad)):
+        util.assert_close("batched grad " + name, a.cpu().numpy(), b.cpu().numpy(), 2e-5)
+
+
+def test_full_size_vs_reference(built_lib, ref_available):
+    """BASELINE config 2/4 size: 300k Gaussians, 1024x1024, one ring camera."""
+    from animatablegaussians_b200 import synthetic as S, camera as C
+    P, img = 300000, 1024
+    g = S.make_gaussians(P)
+    extrs, Ks = S.ring_cameras(16)
+    for v in (0, 5):
+        cb = C.camera_block(extrs[v], Ks[v], img, img)
+        sc = dict(P=P, W=img, H=img, xyz=g["xyz"], scales=g["scales"], rotations=g["rotations"], opacity=g["opacity"],
+                  rgb=g["rgb"], bg=np.zeros(3, np.float32), sh=None, sh_degree=0, cov3D=None, **cb)
+        up = util.upstream_grads(img, img, 40 + v)
+        want = Hn.run_reference(sc, up)
+        got = Hn.run_product(sc, up)
+        rep = Hn.compare("full_v%d" % v, got, want, util.TOL, util.assert_close)
+        print("full", v, {k: "%.1e" % e for k, e in rep.items()})

@@ -81,7 +81,7 @@ def upstream_grads(W, H, seed):
             rng.normal(0, 1, (1, H, W)).astype(np.float32))
 
 
-def run_oracle(sc, grads=None):
+def run_oracle(sc, grads=None, alpha_from=None):
     from oracle.raster_oracle import RasterOracle
     o = RasterOracle()
     color, radii, depth, alpha = o.forward(sc["bg"], sc["xyz"], sc["rgb"], sc["opacity"], sc["scales"], sc["rotations"],
@@ -90,5 +90,5 @@ def run_oracle(sc, grads=None):
                                            campos=sc["campos"])
     out = dict(color=color, radii=radii, depth=depth, alpha=alpha, R=o.num_rendered)
     if grads is not None:
-        out["grads"] = o.backward(*grads)
+        out["grads"] = o.backward(*grads, alpha_override=alpha_from)
     return out
