@@ -1,0 +1,348 @@
+"""AvatarNet for B200 — host-side mirror of the reference's network/avatar.py (`AvatarNet`, avatar.py:16-239),
+gaussians/gaussian_model.py (the parts AvatarNet uses: create_from_pcd + activations, :46-62,115-183) and
+gaussians/gaussian_renderer.py (`render3`, :19-106).
+
+Same constructor options (`random_style`, `with_viewdirs`, `weight_viewdirs`), same attributes the trainer
+touches (SURVEY.md §8b "model boundary"), same `render(items, bg_color, use_pca, use_vae)` signature and return
+keys, same state_dict prefixes (color_net./position_net./other_net./viewdir_net.) — main_avatar.py runs unchanged.
+
+B200-first additions (results identical):
+  * the constant boolean-mask gather `map[cano_smpl_mask]` (avatar.py:97,110,122) uses indices computed once;
+  * transform_cano2live is one fused kernel (lbs.py);
+  * render_views(): V cameras of ONE pose in a single pass — position/other nets and the view-independent
+    prefix of the colour net run once, only the view-dependent tail of the colour net, the view-direction
+    features and the rasterizer run per view, and the rasterizer takes all V views in one batched call.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import camera, lbs
+from . import styleunet_ops as ops
+from .rasterizer import GaussianRasterizer, rasterize_gaussians_batched
+from .styleunet import DualStyleUNet
+
+
+def inverse_sigmoid(x):
+    return torch.log(x / (1 - x))
+
+
+def knn_mean_dist2(points, K=3, chunk=2048):
+    """Mean squared distance to the K nearest neighbours (excluding self) — what the reference gets from
+    pytorch3d.ops.knn_points(K=4)[0][0, :, 1:].mean(-1) (gaussian_model.py:170). Exact, chunked brute force."""
+    N = points.shape[0]
+    out = torch.empty(N, dtype=points.dtype, device=points.device)
+    sq = (points * points).sum(-1)
+    for s in range(0, N, chunk):
+        p = points[s:s + chunk]
+        d2 = (sq[s:s + chunk, None] + sq[None, :] - 2.0 * p @ points.T).clamp_min_(0)
+        vals = torch.topk(d2, K + 1, dim=1, largest=False).values
+        out[s:s + chunk] = vals[:, 1:].mean(-1)
+    return out
+
+
+class GaussianModel:
+    """Canonical Gaussian attributes (constants of the avatar; not an nn.Module in the reference either,
+    gaussian_model.py:44 — SURVEY.md Appendix B.1)."""
+
+    def __init__(self, sh_degree=0):
+        self.max_sh_degree = sh_degree
+        self.scaling_activation = torch.exp
+        self.scaling_inverse_activation = torch.log
+        self.opacity_activation = torch.sigmoid
+        self.inverse_opacity_activation = inverse_sigmoid
+        self.rotation_activation = F.normalize
+
+    def create_from_pcd(self, points, colors=None, spatial_lr_scale=1.0, dist2=None):
+        pts = points.float()
+        if dist2 is None:
+            dist2 = knn_mean_dist2(pts)
+        dist2 = torch.clamp_min(dist2, 0.0000001)
+        self._xyz = pts
+        self._scaling = torch.log(torch.sqrt(dist2))[..., None].repeat(1, 3)
+        self._rotation = torch.zeros((pts.shape[0], 4), device=pts.device)
+        self._rotation[:, 0] = 1
+        self._opacity = inverse_sigmoid(0.1 * torch.ones((pts.shape[0], 1), dtype=torch.float, device=pts.device))
+
+    get_xyz = property(lambda s: s._xyz)
+    get_scaling = property(lambda s: s.scaling_activation(s._scaling))
+    get_scaling_raw = property(lambda s: s._scaling)
+    get_rotation = property(lambda s: s.rotation_activation(s._rotation))
+    get_rotation_raw = property(lambda s: s._rotation)
+    get_opacity = property(lambda s: s.opacity_activation(s._opacity))
+    get_opacity_raw = property(lambda s: s._opacity)
+
+
+def render3(gaussian_vals, bg_color, extr, intr, img_w, img_h, scaling_modifier=1.0):
+    """gaussians/gaussian_renderer.py:19-106 for the colours-precomputed case used by AvatarNet."""
+    means3D = gaussian_vals['positions']
+    screenspace_points = torch.zeros_like(means3D, requires_grad=True) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    rs = camera.make_raster_settings(extr, intr, int(img_w), int(img_h), bg_color, means3D.device, scaling_modifier,
+                                     gaussian_vals.get('max_sh_degree', 0))
+    assert not ('colors' in gaussian_vals and 'shs' in gaussian_vals), "Cannot use both color and SH!"
+    rendered_image, radii, rendered_depth, rendered_alpha = GaussianRasterizer(raster_settings=rs)(
+        means3D=means3D, means2D=screenspace_points, shs=gaussian_vals.get('shs'), colors_precomp=gaussian_vals.get('colors'),
+        opacities=gaussian_vals['opacity'], scales=gaussian_vals['scales'], rotations=gaussian_vals['rotations'],
+        cov3D_precomp=None)
+    return {"render": rendered_image, "depth": rendered_depth, "mask": rendered_alpha,
+            "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii}
+
+
+class AvatarNet(nn.Module):
+    def __init__(self, opt, canonical=None, device=None):
+        """canonical: dict(cano_smpl_map (H,2H,3), cano_nml_map (H,2H,3), lbs (N,J)[, dist2 (N,)]) of numpy arrays.
+        When None the three files are read from config.opt['train']['data']['data_dir'] exactly like the
+        reference (avatar.py:27,31,43)."""
+        super().__init__()
+        self.opt = opt
+        self.random_style = opt.get('random_style', False)
+        self.with_viewdirs = opt.get('with_viewdirs', True)
+        if device is None:
+            try:
+                import config  # the reference's global config module, when running under main_avatar.py
+                device = config.device
+            except Exception:
+                device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
+        self.device_ = torch.device(device)
+        if canonical is None:
+            canonical = self._load_canonical_from_config()
+        dev = self.device_
+        self.max_sh_degree = 0
+        self.cano_gaussian_model = GaussianModel(sh_degree=self.max_sh_degree)
+        self.cano_smpl_map = torch.from_numpy(np.asarray(canonical['cano_smpl_map'])).to(torch.float32).to(dev)
+        self.cano_smpl_mask = torch.linalg.norm(self.cano_smpl_map, dim=-1) > 0.
+        self.init_points = self.cano_smpl_map[self.cano_smpl_mask]
+        self.lbs = torch.from_numpy(np.asarray(canonical['lbs'])).to(torch.float32).to(dev).contiguous()
+        d2 = canonical.get('dist2')
+        self.cano_gaussian_model.create_from_pcd(self.init_points, None, spatial_lr_scale=2.5,
+                                                 dist2=None if d2 is None else torch.from_numpy(np.asarray(d2)).float().to(dev))
+        size = self.cano_smpl_map.shape[0]
+        self.map_size = size
+        self.color_net = DualStyleUNet(inp_size=size // 2, inp_ch=3, out_ch=3, out_size=size, style_dim=512, n_mlp=2)
+        self.position_net = DualStyleUNet(inp_size=size // 2, inp_ch=3, out_ch=3, out_size=size, style_dim=512, n_mlp=2)
+        self.other_net = DualStyleUNet(inp_size=size // 2, inp_ch=3, out_ch=8, out_size=size, style_dim=512, n_mlp=2)
+        mk = lambda n: torch.ones([1, n.style_dim], dtype=torch.float32, device=dev) / np.sqrt(n.style_dim)
+        self.color_style, self.position_style, self.other_style = mk(self.color_net), mk(self.position_net), mk(self.other_net)
+        if self.with_viewdirs:
+            self.cano_nml_map = torch.from_numpy(np.asarray(canonical['cano_nml_map'])).to(torch.float32).to(dev)
+            self.cano_nmls = self.cano_nml_map[self.cano_smpl_mask]
+            self.viewdir_net = nn.Sequential(nn.Conv2d(1, 64, 4, 2, 1), nn.LeakyReLU(0.2, inplace=True), nn.Conv2d(64, 128, 4, 2, 1))
+        # constant gather indices of the mask (row-major order == boolean-mask order of the reference)
+        rc = torch.nonzero(self.cano_smpl_mask)
+        self._half = (rc[:, 1] >= size).long()
+        self._pix = rc[:, 0] * size + (rc[:, 1] % size)
+        self._flat = rc[:, 0] * (2 * size) + rc[:, 1]
+
+    @staticmethod
+    def _load_canonical_from_config():
+        import cv2 as cv
+        import config
+        d = config.opt['train']['data']['data_dir'] + '/smpl_pos_map/'
+        return dict(cano_smpl_map=cv.imread(d + 'cano_smpl_pos_map.exr', cv.IMREAD_UNCHANGED),
+                    cano_nml_map=cv.imread(d + 'cano_smpl_nml_map.exr', cv.IMREAD_UNCHANGED),
+                    lbs=np.load(d + 'init_pts_lbs.npy'))
+
+    # ------------------------------------------------------------------ map -> per-Gaussian gather
+    def _gather(self, maps):
+        """(1, 2C, S, S) front|back maps -> (N, C) in cano_smpl_mask order; == cat on W, permute, [mask]."""
+        C = maps.shape[1] // 2
+        m = maps[0].reshape(2, C, -1)
+        return m[self._half, :, self._pix]
+
+    def _as_map(self, maps):
+        front, back = torch.split(maps, [maps.shape[1] // 2] * 2, 1)
+        return torch.cat([front, back], 3)[0].permute(1, 2, 0)
+
+    # ------------------------------------------------------------------ reference methods
+    def transform_cano2live(self, gaussian_vals, items):
+        pos, rot = lbs.transform_cano2live(self.lbs, items['cano2live_jnt_mats'], gaussian_vals['positions'],
+                                           gaussian_vals['rotations'])
+        gaussian_vals['positions'], gaussian_vals['rotations'] = pos, rot
+        return gaussian_vals
+
+    def get_positions(self, pose_map, return_map=False):
+        position_map, _ = self.position_net([self.position_style], pose_map[None], randomize_noise=False)
+        delta_position = 0.05 * self._gather(position_map)
+        positions = delta_position + self.cano_gaussian_model.get_xyz
+        if return_map:
+            return positions, self._as_map(position_map)
+        return positions
+
+    def _activate_others(self, others):
+        g = self.cano_gaussian_model
+        opacity, scales, rotations = torch.split(others, [1, 3, 4], 1)
+        opacity = g.opacity_activation(opacity + g.get_opacity_raw)
+        scales = g.scaling_activation(scales + g.get_scaling_raw)
+        rotations = g.rotation_activation(rotations + g.get_rotation_raw)
+        return opacity, scales, rotations
+
+    def get_others(self, pose_map):
+        other_map, _ = self.other_net([self.other_style], pose_map[None], randomize_noise=False)
+        return self._activate_others(self._gather(other_map))
+
+    def _color_style(self):
+        return torch.rand_like(self.color_style) if self.random_style and self.training else self.color_style
+
+    def get_colors(self, pose_map, front_viewdirs=None, back_viewdirs=None):
+        color_map, _ = self.color_net([self._color_style()], pose_map[None], randomize_noise=False,
+                                      view_feature1=front_viewdirs, view_feature2=back_viewdirs)
+        return self._gather(color_map), self._as_map(color_map)
+
+    def _viewdir_maps(self, items, live_pts, live_nmls):
+        cam_pos = -torch.matmul(torch.linalg.inv(items['extr'][:3, :3]), items['extr'][:3, 3])
+        viewdirs = F.normalize(cam_pos[None] - live_pts, dim=-1, eps=1e-3)
+        if self.training:
+            viewdirs += torch.randn(*viewdirs.shape).to(viewdirs) * 0.1
+        viewdirs = F.normalize(viewdirs, dim=-1, eps=1e-3)
+        viewdirs = (live_nmls * viewdirs).sum(-1)
+        viewdirs_map = torch.zeros(self.cano_nml_map.shape[0] * self.cano_nml_map.shape[1], dtype=viewdirs.dtype, device=viewdirs.device)
+        viewdirs_map[self._flat] = viewdirs
+        viewdirs_map = viewdirs_map.view(1, 1, *self.cano_nml_map.shape[:2])
+        viewdirs_map = F.interpolate(viewdirs_map, None, 0.5, 'nearest')
+        half = viewdirs_map.shape[-1] // 2
+        return torch.split(viewdirs_map, [half, half], -1)
+
+    def get_viewdir_feat(self, items, live=None):
+        with torch.no_grad():
+            if live is None:
+                live = lbs.skin_points(self.lbs, items['cano2live_jnt_mats'], self.init_points, self.cano_nmls)
+            front_viewdirs, back_viewdirs = self._viewdir_maps(items, *live)
+        w = self.opt.get('weight_viewdirs', 1.)
+        return w * self.viewdir_net(front_viewdirs), w * self.viewdir_net(back_viewdirs)
+
+    def get_pose_map(self, items):
+        live_pts = lbs.skin_points(self.lbs, items['cano2live_jnt_mats_woRoot'], self.init_points)
+        live_pos_map = torch.zeros_like(self.cano_smpl_map)
+        live_pos_map.view(-1, 3)[self._flat] = live_pts
+        live_pos_map = F.interpolate(live_pos_map.permute(2, 0, 1)[None], None, [0.5, 0.5], mode='nearest')[0]
+        half = live_pos_map.shape[2] // 2
+        live_pos_map = torch.cat(torch.split(live_pos_map, [half, half], 2), 0)
+        items.update({'smpl_pos_map': live_pos_map})
+        return live_pos_map
+
+    def _bg(self, bg_color):
+        return torch.from_numpy(np.asarray(bg_color)).to(torch.float32).to(self.device_)
+
+    def render(self, items, bg_color=(0., 0., 0.), use_pca=False, use_vae=False):
+        """Note that no batch index in items. (avatar.py:161-239)"""
+        bg_color = self._bg(bg_color)
+        pose_map = items['smpl_pos_map'][:3]
+        assert not (use_pca and use_vae), "Cannot use both PCA and VAE!"
+        if use_pca:
+            pose_map = items['smpl_pos_map_pca'][:3]
+        if use_vae:
+            pose_map = items['smpl_pos_map_vae'][:3]
+        cano_pts, pos_map = self.get_positions(pose_map, return_map=True)
+        opacity, scales, rotations = self.get_others(pose_map)
+        if self.with_viewdirs:
+            front_viewdirs, back_viewdirs = self.get_viewdir_feat(items)
+        else:
+            front_viewdirs, back_viewdirs = None, None
+        colors, color_map = self.get_colors(pose_map, front_viewdirs, back_viewdirs)
+        gaussian_vals = {'positions': cano_pts, 'opacity': opacity, 'scales': scales, 'rotations': rotations,
+                         'colors': colors, 'max_sh_degree': self.max_sh_degree}
+        nonrigid_offset = gaussian_vals['positions'] - self.init_points
+        gaussian_vals = self.transform_cano2live(gaussian_vals, items)
+        render_ret = render3(gaussian_vals, bg_color, items['extr'], items['intr'], items['img_w'], items['img_h'])
+        ret = {'rgb_map': render_ret['render'].permute(1, 2, 0), 'mask_map': render_ret['mask'].permute(1, 2, 0),
+               'offset': nonrigid_offset, 'pos_map': pos_map}
+        if not self.training:
+            ret.update({'cano_tex_map': color_map, 'posed_gaussians': gaussian_vals})
+        return ret
+
+    # ------------------------------------------------------------------ view batch (one pose, V cameras)
+    def render_views(self, items, extrs, intrs, img_w, img_h, bg_color=(0., 0., 0.), return_depth=False):
+        """items: pose-level entries ('smpl_pos_map', 'cano2live_jnt_mats'); extrs/intrs: V host (numpy) camera
+        matrices.  Returns rgb_maps (V,H,W,3), mask_maps (V,H,W,1) [, depth_maps (V,H,W,1)], offset, pos_map —
+        per view identical to render() with that camera."""
+        V = len(extrs)
+        dev = self.device_
+        bg = self._bg(bg_color)
+        pose_map = items['smpl_pos_map'][:3]
+        cano_pts, pos_map = self.get_positions(pose_map, return_map=True)
+        opacity, scales, rotations = self.get_others(pose_map)
+        nonrigid_offset = cano_pts - self.init_points
+        if self.with_viewdirs:
+            with torch.no_grad():
+                live = lbs.skin_points(self.lbs, items['cano2live_jnt_mats'], self.init_points, self.cano_nmls)
+            prefix = self.color_net.forward_prefix([self._color_style()], pose_map[None])
+            cols = []
+            for v in range(V):
+                it = {'extr': torch.as_tensor(np.asarray(extrs[v]), dtype=torch.float32, device=dev)}
+                fv, bv = self.get_viewdir_feat(it, live)
+                cols.append(self._gather(self.color_net.forward_view_tail(prefix, fv, bv)))
+            colors = torch.stack(cols, 0)
+        else:
+            colors, _ = self.get_colors(pose_map)
+        pos, rot = lbs.transform_cano2live(self.lbs, items['cano2live_jnt_mats'], cano_pts, rotations)
+        bs = camera.make_batched_settings(extrs, intrs, int(img_w), int(img_h), bg, dev)
+        color, radii, depth, alpha = rasterize_gaussians_batched(pos, None, None, colors, opacity, scales, rot, None, bs)
+        ret = {'rgb_maps': color.permute(0, 2, 3, 1), 'mask_maps': alpha.permute(0, 2, 3, 1), 'offset': nonrigid_offset,
+               'pos_map': pos_map, 'radii': radii}
+        if return_depth:
+            ret['depth_maps'] = depth.permute(0, 2, 3, 1)
+        return ret
+
+
+@torch.no_grad()
+def emulate_pretrained_heads(net, pose_map, pos_std=0.1, other_std=0.3, color_std=0.3, opacity_shift=3.2):
+    """Synthetic stand-in for the reference's pretraining stage (main_avatar.py:126-164,266-326), which fits the
+    three nets to the canonical attributes (zero offsets, canonical scale/rotation/opacity) BEFORE any rendering.
+    Random-init StyleGAN heads emit O(1..10) maps -> metre-sized, screen-filling Gaussians that no real training
+    step ever rasterises.  The output maps are linear in the ToRGB weights/biases, so scaling those scales the maps
+    exactly: position maps to std `pos_std` (x0.05 => ~5 mm offsets), other maps to `other_std`, colour maps to
+    `color_std`, and the opacity logit is shifted by `opacity_shift` (logit(0.1)+3.2 ~ 1.0)."""
+    for name, style, std in (("position_net", net.position_style, pos_std), ("other_net", net.other_style, other_std),
+                             ("color_net", net.color_style, color_std)):
+        n = getattr(net, name)
+        m, _ = n([style], pose_map[None], randomize_noise=False)
+        f = float(std / m.float().std().clamp_min(1e-12))
+        for rgbs in (n.to_rgbs1, n.to_rgbs2):
+            for t in rgbs:
+                t.conv.weight.mul_(f)
+                t.bias.mul_(f)
+    for rgbs in (net.other_net.to_rgbs1, net.other_net.to_rgbs2):
+        rgbs[-1].bias[0, 0] += 2.0 * opacity_shift  # LL sub-band of channel 0: the Haar synthesis halves it
+
+
+def synthetic_canonical(P, size=1024, J=55, seed=31359):
+    """Canonical inputs of AvatarNet for the synthetic capsule avatar: position / normal maps of
+    shape (size, 2*size, 3) with exactly P valid pixels (front half | back half) and dense (P,J) LBS weights."""
+    from . import synthetic as S
+    half = (P + 1) // 2
+    # valid pixels: a centred rectangle-ish silhouette per half, row-major, first `half` (front) / `P-half` (back)
+    h_rows = int(math.ceil(math.sqrt(half * 1.7 / 0.45)))
+    h_cols = int(math.ceil(half / h_rows))
+    assert h_rows <= size and h_cols <= size, "P too large for the map"
+    r0, c0 = (size - h_rows) // 2, (size - h_cols) // 2
+    pos = np.zeros((size, 2 * size, 3), np.float32)
+    nml = np.zeros((size, 2 * size, 3), np.float32)
+    rng = np.random.default_rng(seed)
+    pts, spacing = S.capsule_points(P, rng)
+    # place points: front half then back half, each filling its silhouette row-major
+    rr, cc = np.meshgrid(np.arange(h_rows), np.arange(h_cols), indexing="ij")
+    rr, cc = rr.reshape(-1), cc.reshape(-1)
+    order_f = np.arange(half)
+    order_b = np.arange(P - half)
+    # guard against exact-zero positions (mask = norm > 0)
+    pts = pts + (np.abs(pts).sum(1, keepdims=True) == 0) * 1e-6
+    pos[r0 + rr[order_f], c0 + cc[order_f]] = pts[:half]
+    pos[r0 + rr[order_b], size + c0 + cc[order_b]] = pts[half:]
+    n = pts.copy()
+    n[:, 1] = 0
+    n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-6)
+    nml[r0 + rr[order_f], c0 + cc[order_f]] = n[:half]
+    nml[r0 + rr[order_b], size + c0 + cc[order_b]] = n[half:]
+    # boolean-mask order = row-major over the (size, 2*size) map
+    mask = np.linalg.norm(pos, axis=-1) > 0
+    ordered = pos[mask]
+    w, mats = S.make_skinning(ordered, J=J, seed=seed)
+    dist2 = np.full((ordered.shape[0],), float(spacing) ** 2, np.float32)
+    return dict(cano_smpl_map=pos, cano_nml_map=nml, lbs=w, dist2=dist2), mats

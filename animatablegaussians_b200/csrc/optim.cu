@@ -1,0 +1,62 @@
+// Fused Adam over one flat fp32 bucket (include/agr_optim.h). Pure HBM streaming: 16 B read + 12 B (+4 B
+// zero-fill of the gradient) written per parameter, 128-bit accesses, grid sized to the SM count.
+#include "../../include/agr_optim.h"
+#include "../../include/agr_rasterizer.h"
+#include <cuda_runtime.h>
+
+namespace agr {
+__global__ void __launch_bounds__(256) adam_kernel(int64_t n4, int64_t n, float4* __restrict__ p, float4* __restrict__ g,
+                                                  float4* __restrict__ m, float4* __restrict__ v, float lr_c, float b1,
+                                                  float b2, float eps, float inv_sqrt_bc2, float gs, int zero) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 P = p[i], G = g[i], M = m[i], V = v[i];
+        float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = gg[k] * gs;
+            mm[k] = b1 * mm[k] + (1.f - b1) * gk;
+            vv[k] = b2 * vv[k] + (1.f - b2) * gk * gk;
+            pp[k] -= lr_c * mm[k] / (sqrtf(vv[k]) * inv_sqrt_bc2 + eps);
+        }
+        p[i] = P; m[i] = M; v[i] = V;
+        if (zero) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // tail (n % 4 elements) handled by the first threads of block 0
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = n4 * 4 + threadIdx.x;
+        float* P = reinterpret_cast<float*>(p); float* G = reinterpret_cast<float*>(g);
+        float* M = reinterpret_cast<float*>(m); float* V = reinterpret_cast<float*>(v);
+        const float gk = G[i] * gs;
+        M[i] = b1 * M[i] + (1.f - b1) * gk;
+        V[i] = b2 * V[i] + (1.f - b2) * gk * gk;
+        P[i] -= lr_c * M[i] / (sqrtf(V[i]) * inv_sqrt_bc2 + eps);
+        if (zero) G[i] = 0.f;
+    }
+}
+}  // namespace agr
+
+extern "C" int agr_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                             float beta2, float eps, int32_t step, float grad_scale, int32_t zero_grad, void* cuda_stream) {
+    if (n < 0 || step < 1) return AGR_ERR_INVALID_ARGUMENT;
+    if (n == 0) return AGR_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq) return AGR_ERR_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+         reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+        return AGR_ERR_INVALID_ARGUMENT;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float lr_c = (float)(lr / bc1);
+    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    if (blocks < 1) blocks = 1;
+    agr::adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        n4, n, reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(exp_avg),
+        reinterpret_cast<float4*>(exp_avg_sq), lr_c, beta1, beta2, eps, inv_sqrt_bc2, grad_scale, zero_grad);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}

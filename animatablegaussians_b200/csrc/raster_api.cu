@@ -94,12 +94,12 @@ int agr_raster_forward(const AgrRasterForwardArgs* a, void* cuda_stream) {
 
         // number of (tile, Gaussian) instances; the reference does the same blocking read
         // (rasterizer_impl.cu:281-282) to size its binning buffer.
-        uint32_t r32 = 0;
-        if (cuda_fail(cudaMemcpyAsync(&r32, gw.offsets + n - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s))) return AGR_ERR_CUDA;
+        uint64_t r64 = 0;
+        if (cuda_fail(cudaMemcpyAsync(&r64, gw.offsets + n - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, s))) return AGR_ERR_CUDA;
         if (cuda_fail(cudaStreamSynchronize(s))) return AGR_ERR_CUDA;
-        R = r32;
+        R = (int64_t)r64;
         *a->num_rendered = R;
-        if (R > a->capacity) return AGR_ERR_BINNING_CAPACITY;
+        if (R > a->capacity || R >= ((int64_t)1 << 32)) return AGR_ERR_BINNING_CAPACITY;
 
         if (R > 0) {
             bw = carve_binning(a->binning_ws, (size_t)a->capacity);

@@ -8,9 +8,16 @@
 
 namespace agr {
 
+struct U32ToU64 {
+    __host__ __device__ __forceinline__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; }
+};
+using WideIter = cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*>;
+
+// 64-bit running sum: V*P*tiles can exceed 2^32 for degenerate (screen-filling) inputs and must be
+// reported as a capacity error, not wrap around.
 size_t scan_temp_bytes(size_t n) {
     size_t bytes = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    cub::DeviceScan::InclusiveSum(nullptr, bytes, WideIter((const uint32_t*)nullptr, U32ToU64()), (uint64_t*)nullptr, (int)n);
     return bytes;
 }
 
@@ -21,8 +28,8 @@ size_t sort_temp_bytes(size_t n) {
     return bytes;
 }
 
-cudaError_t inclusive_scan_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t s) {
-    return cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, in, out, (int)n, s);
+cudaError_t inclusive_scan_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint64_t* out, size_t n, cudaStream_t s) {
+    return cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, WideIter(in, U32ToU64()), out, (int)n, s);
 }
 
 cudaError_t sort_pairs_u64_u32(void* tmp, size_t tmp_bytes, const uint64_t* kin, uint64_t* kout,

@@ -168,7 +168,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 struct GeomWs {  // carved from geom_ws
     GeomRec* rec;          // V*P
     uint32_t* tiles;       // V*P   tiles touched
-    uint32_t* offsets;     // V*P   inclusive scan of tiles
+    uint64_t* offsets;     // V*P   inclusive scan of tiles (64-bit: cannot wrap)
     float* rgb;            // V*P*3 (SH only)
     uint8_t* clamped;      // V*P*3 (SH only)
     void* scan_tmp; size_t scan_tmp_bytes;

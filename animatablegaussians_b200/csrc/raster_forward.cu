@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) duplicate_kernel(DuplicateParams p) {
     if (radius <= 0) return;
     const uint32_t v = (uint32_t)(vg / p.P);
     const uint32_t g = (uint32_t)(vg - (size_t)v * p.P);
-    uint32_t off = (vg == 0) ? 0u : p.ws_offsets[vg - 1];
+    uint64_t off = (vg == 0) ? 0ull : p.ws_offsets[vg - 1];
     const TileRect r = tile_rect(rec.a.x, rec.a.y, radius, p.grid_x, p.grid_y);
     const uint32_t depth_bits = __float_as_uint(rec.b.z);
     const uint32_t tile_base = v * p.grid_x * p.grid_y;

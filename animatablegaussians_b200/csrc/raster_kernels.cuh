@@ -63,7 +63,7 @@ struct DuplicateParams {
     int P, V;
     uint32_t grid_x, grid_y;
     uint64_t capacity;
-    const GeomRec* ws_rec; const uint32_t* ws_offsets;
+    const GeomRec* ws_rec; const uint64_t* ws_offsets;
     uint64_t* keys; uint32_t* vals;
 };
 
@@ -115,7 +115,7 @@ void launch_blend_bwd(const BlendBwdParams&, cudaStream_t);
 void launch_preprocess_bwd(const PreprocessBwdParams&, const ViewScalars&, cudaStream_t);
 
 // CUB-backed primitives (raster_binning.cu)
-cudaError_t inclusive_scan_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t);
+cudaError_t inclusive_scan_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint64_t* out, size_t n, cudaStream_t);
 cudaError_t sort_pairs_u64_u32(void* tmp, size_t tmp_bytes, const uint64_t* kin, uint64_t* kout,
                                const uint32_t* vin, uint32_t* vout, size_t n, int end_bit, cudaStream_t);
 

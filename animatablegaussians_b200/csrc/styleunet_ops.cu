@@ -1,0 +1,442 @@
+// StyleUNet glue operators on NHWC activations (fp32 / bf16), include/agr_styleunet.h.
+//
+// All of these are HBM-streaming kernels: each output element is produced from a handful of neighbouring
+// inputs, so the design rule is "touch HBM once, 128-bit accesses along the channel axis".
+//   upfirdn2d  : reference upfirdn2d_kernel.cu:107-207 stages an input tile + taps in shared memory for a
+//                (major,H,W,minor=1) layout; in NHWC the channel axis is contiguous, a thread owns one output
+//                pixel x 8 (bf16) / 4 (fp32) channels and the <=16 taps hit L1/L2 (neighbouring threads share them).
+//   haar       : the four 2x2 sub-band filters of dual_styleunet.py:374-425 applied in ONE pass (reference: 4
+//                upfirdn2d launches + cat / 4 launches + 3 adds).
+//   bias_act   : fused_bias_act_kernel.cu:18-65 (act=3) fused with NoiseInjection (dual_styleunet.py:303-313); the
+//                backward also produces the bias / noise-weight reductions the reference computes with a
+//                separate .sum().
+//   modweight  : dual_styleunet.py:256-265 in one pass per layer, writing the KRSC layout the implicit GEMM wants.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "../../include/agr_rasterizer.h"
+#include "../../include/agr_styleunet.h"
+
+namespace agr {
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { static constexpr int N = 4; using V = float4; };
+template <> struct VecOf<__nv_bfloat16> { static constexpr int N = 8; using V = uint4; };
+
+__device__ __forceinline__ void unpack(const float4& v, float* f) { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+__device__ __forceinline__ void unpack(const uint4& v, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void pack(const float* f, float4& v) { v = make_float4(f[0], f[1], f[2], f[3]); }
+__device__ __forceinline__ void pack(const float* f, uint4& v) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+}
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// ------------------------------------------------------------------------------------------------ upfirdn2d
+struct FirParams {
+    float taps[64];
+    int kh, kw, up, down, pad_x0, pad_y0;
+};
+
+template <typename T, bool VECTOR>
+__global__ void __launch_bounds__(256) upfirdn_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C,
+                                                     int outH, int outW, FirParams fp) {
+    constexpr int VN = VECTOR ? VecOf<T>::N : 1;
+    const int cv = C / VN;
+    const int64_t total = (int64_t)N * outH * outW * cv;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % cv);
+    int64_t p = idx / cv;
+    const int ox = (int)(p % outW); p /= outW;
+    const int oy = (int)(p % outH);
+    const int n = (int)(p / outH);
+    float acc[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+    const int by = oy * fp.down - fp.pad_y0, bx = ox * fp.down - fp.pad_x0;
+    for (int ky = 0; ky < fp.kh; ++ky) {
+        const int uy = by + ky;
+        if (uy < 0 || (uy % fp.up) != 0) continue;
+        const int iy = uy / fp.up;
+        if (iy >= H) continue;
+        for (int kx = 0; kx < fp.kw; ++kx) {
+            const int ux = bx + kx;
+            if (ux < 0 || (ux % fp.up) != 0) continue;
+            const int ix = ux / fp.up;
+            if (ix >= W) continue;
+            const float t = fp.taps[ky * fp.kw + kx];
+            const T* src = x + (((int64_t)n * H + iy) * W + ix) * C + (int64_t)c * VN;
+            if (VECTOR) {
+                float f[VN];
+                unpack(*reinterpret_cast<const typename VecOf<T>::V*>(src), f);
+#pragma unroll
+                for (int i = 0; i < VN; ++i) acc[i] += t * f[i];
+            } else {
+                acc[0] += t * to_f(src[0]);
+            }
+        }
+    }
+    T* dst = y + (((int64_t)n * outH + oy) * outW + ox) * C + (int64_t)c * VN;
+    if (VECTOR) {
+        typename VecOf<T>::V v;
+        pack(acc, v);
+        *reinterpret_cast<typename VecOf<T>::V*>(dst) = v;
+    } else {
+        dst[0] = from_f<T>(acc[0]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ haar
+// analysis: x (H,W,C) -> y (H/2,W/2,4C);  synthesis: x (H,W,4C) -> y (2H,2W,C).  Orthonormal: each is the
+// other's adjoint, so backward(dwt) = synthesis and backward(iwt) = analysis.
+template <typename T, bool VECTOR, bool ANALYSIS>
+__global__ void __launch_bounds__(256) haar_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C) {
+    constexpr int VN = VECTOR ? VecOf<T>::N : 1;
+    // C = channels of the SPATIALLY LARGER tensor (the image side); Hs,Ws = size of the sub-band side
+    const int Hs = ANALYSIS ? H / 2 : H, Ws = ANALYSIS ? W / 2 : W;
+    const int Ci = ANALYSIS ? C : C / 4;
+    const int cv = Ci / VN;
+    const int64_t total = (int64_t)N * Hs * Ws * cv;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % cv) * VN;
+    int64_t p = idx / cv;
+    const int j = (int)(p % Ws); p /= Ws;
+    const int i = (int)(p % Hs);
+    const int n = (int)(p / Hs);
+    const int Hi = Hs * 2, Wi = Ws * 2;
+    float a[4][VN];  // image pixels (0,0) (0,1) (1,0) (1,1) or sub-bands ll lh hl hh
+    using V = typename VecOf<T>::V;
+    auto ld = [&](const T* ptr, float* f) {
+        if (VECTOR) unpack(*reinterpret_cast<const V*>(ptr), f); else f[0] = to_f(ptr[0]);
+    };
+    auto st = [&](T* ptr, const float* f) {
+        if (VECTOR) { V v; pack(f, v); *reinterpret_cast<V*>(ptr) = v; } else ptr[0] = from_f<T>(f[0]);
+    };
+    if (ANALYSIS) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            ld(x + (((int64_t)n * Hi + 2 * i + (q >> 1)) * Wi + 2 * j + (q & 1)) * Ci + c, a[q]);
+        float o[4][VN];
+#pragma unroll
+        for (int v = 0; v < VN; ++v) {
+            const float x00 = a[0][v], x01 = a[1][v], x10 = a[2][v], x11 = a[3][v];
+            o[0][v] = 0.5f * (x00 + x01 + x10 + x11);
+            o[1][v] = 0.5f * (x00 + x01 - x10 - x11);
+            o[2][v] = 0.5f * (x00 - x01 + x10 - x11);
+            o[3][v] = 0.5f * (x00 - x01 - x10 + x11);
+        }
+        T* dst = y + (((int64_t)n * Hs + i) * Ws + j) * (4 * Ci);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) st(dst + b * Ci + c, o[b]);
+    } else {
+        const T* src = x + (((int64_t)n * Hs + i) * Ws + j) * (4 * Ci);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) ld(src + b * Ci + c, a[b]);
+        float o[4][VN];
+#pragma unroll
+        for (int v = 0; v < VN; ++v) {
+            const float ll = a[0][v], lh = a[1][v], hl = a[2][v], hh = a[3][v];
+            o[0][v] = 0.5f * (ll + lh + hl + hh);
+            o[1][v] = 0.5f * (ll + lh - hl - hh);
+            o[2][v] = 0.5f * (ll - lh + hl - hh);
+            o[3][v] = 0.5f * (ll - lh - hl + hh);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            st(y + (((int64_t)n * Hi + 2 * i + (q >> 1)) * Wi + 2 * j + (q & 1)) * Ci + c, o[q]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ bias_act
+constexpr float kSqrt2 = 1.4142135623730951f;
+
+template <typename T, bool VECTOR>
+__global__ void __launch_bounds__(256) bias_act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t pixels, int C,
+                                                          const float* __restrict__ bias, const float* __restrict__ noise,
+                                                          const float* __restrict__ noise_w, int activate) {
+    constexpr int VN = VECTOR ? VecOf<T>::N : 1;
+    const int cv = C / VN;
+    const int64_t total = pixels * cv;
+    const float nw = (noise && noise_w) ? noise_w[0] : 0.f;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cv) * VN;
+        const int64_t p = idx / cv;
+        const float add = noise ? nw * noise[p] : 0.f;
+        float f[VN];
+        if (VECTOR) unpack(*reinterpret_cast<const typename VecOf<T>::V*>(x + p * C + c), f); else f[0] = to_f(x[p * C + c]);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+            float v = f[i] + add + (bias ? bias[c + i] : 0.f);
+            if (activate) v = (v > 0.f ? v : v * 0.2f) * kSqrt2;
+            f[i] = v;
+        }
+        if (VECTOR) { typename VecOf<T>::V v; pack(f, v); *reinterpret_cast<typename VecOf<T>::V*>(y + p * C + c) = v; }
+        else y[p * C + c] = from_f<T>(f[0]);
+    }
+}
+
+// Each block owns a slab of pixels; thread = (channel vector, pixel lane). Per-channel partial sums are reduced
+// in shared memory and added with one atomic per channel per block.
+template <typename T, bool VECTOR>
+__global__ void __launch_bounds__(256) bias_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx,
+                                                          int64_t pixels, int C, const float* __restrict__ noise,
+                                                          float* __restrict__ d_bias, float* __restrict__ d_noise_w,
+                                                          int activate, int pixels_per_block) {
+    constexpr int VN = VECTOR ? VecOf<T>::N : 1;
+    extern __shared__ float s_red[];  // C floats (bias) + 1 (noise)
+    const int cv = C / VN;
+    for (int i = threadIdx.x; i < C + 1; i += blockDim.x) s_red[i] = 0.f;
+    __syncthreads();
+    const int64_t p0 = (int64_t)blockIdx.x * pixels_per_block;
+    const int64_t p1 = min(pixels, p0 + pixels_per_block);
+    const int lanes = blockDim.x / cv > 0 ? blockDim.x / cv : 1;   // pixel lanes per block
+    const int my_c = (threadIdx.x % cv) * VN;
+    const int my_lane = threadIdx.x / cv;
+    float bsum[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) bsum[i] = 0.f;
+    float nsum = 0.f;
+    if (my_lane < lanes) {
+        for (int64_t p = p0 + my_lane; p < p1; p += lanes) {
+            float g[VN], o[VN];
+            if (VECTOR) {
+                unpack(*reinterpret_cast<const typename VecOf<T>::V*>(dy + p * C + my_c), g);
+                if (activate) unpack(*reinterpret_cast<const typename VecOf<T>::V*>(y + p * C + my_c), o);
+            } else {
+                g[0] = to_f(dy[p * C + my_c]);
+                if (activate) o[0] = to_f(y[p * C + my_c]);
+            }
+            float psum = 0.f;
+#pragma unroll
+            for (int i = 0; i < VN; ++i) {
+                if (activate) g[i] *= (o[i] > 0.f ? kSqrt2 : 0.2f * kSqrt2);
+                bsum[i] += g[i];
+                psum += g[i];
+            }
+            if (noise) nsum += psum * noise[p];
+            if (VECTOR) { typename VecOf<T>::V v; pack(g, v); *reinterpret_cast<typename VecOf<T>::V*>(dx + p * C + my_c) = v; }
+            else dx[p * C + my_c] = from_f<T>(g[0]);
+        }
+        if (d_bias) {
+#pragma unroll
+            for (int i = 0; i < VN; ++i) atomicAdd(&s_red[my_c + i], bsum[i]);
+        }
+        if (d_noise_w && noise) atomicAdd(&s_red[C], nsum);
+    }
+    __syncthreads();
+    if (d_bias) for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&d_bias[i], s_red[i]);
+    if (d_noise_w && noise && threadIdx.x == 0) atomicAdd(d_noise_w, s_red[C]);
+}
+
+// ------------------------------------------------------------------------------------------------ modweight
+// One block per output channel. w: (Cout, Cin, k, k) fp32.
+template <typename T>
+__global__ void __launch_bounds__(256) modweight_fwd_kernel(const float* __restrict__ w, const float* __restrict__ s, float scale,
+                                                           int Cout, int Cin, int kk, int demodulate, int transpose_io,
+                                                           T* __restrict__ w_out, float* __restrict__ demod_out) {
+    __shared__ float s_part[32];
+    __shared__ float s_demod;
+    const int co = blockIdx.x;
+    const int n = Cin * kk;
+    const float* wr = w + (size_t)co * n;
+    float d = 1.f;
+    if (demodulate) {
+        float acc = 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float u = scale * wr[i] * s[i / kk];
+            acc += u * u;
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.f;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (threadIdx.x == 0) { s_demod = rsqrtf(v + 1e-8f); if (demod_out) demod_out[co] = s_demod; }
+        }
+        __syncthreads();
+        d = s_demod;
+    }
+    // output index: KRSC [co][t][ci]  or (transpose_io) [ci][t][co]
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int t = i / Cin, ci = i - t * Cin;  // iterate with ci fastest for coalesced KRSC writes
+        const float u = scale * wr[ci * kk + t] * s[ci] * d;
+        const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
+        w_out[o] = from_f<T>(u);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) modweight_bwd_kernel(const float* __restrict__ w, const float* __restrict__ s, float scale,
+                                                           int Cout, int Cin, int kk, int demodulate, int transpose_io,
+                                                           const T* __restrict__ d_wout, const float* __restrict__ demod,
+                                                           float* __restrict__ d_w, float* __restrict__ d_s) {
+    __shared__ float s_part[32];
+    __shared__ float s_dot;
+    const int co = blockIdx.x;
+    const int n = Cin * kk;
+    const float* wr = w + (size_t)co * n;
+    const float d = demodulate ? demod[co] : 1.f;
+    float dot = 0.f;  // sum_i dW'_i * u_i
+    if (demodulate) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int t = i / Cin, ci = i - t * Cin;
+            const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
+            dot += to_f(d_wout[o]) * (scale * wr[ci * kk + t] * s[ci]);
+        }
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = dot;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.f;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (threadIdx.x == 0) s_dot = v;
+        }
+        __syncthreads();
+        dot = s_dot;
+    }
+    const float d3dot = demodulate ? d * d * d * dot : 0.f;
+    // thread owns input channels ci = threadIdx.x, +blockDim.x, ... so d_s needs one atomic per (co, ci)
+    for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+        float ds = 0.f;
+        for (int t = 0; t < kk; ++t) {
+            const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
+            const float wv = wr[ci * kk + t];
+            const float u = scale * wv * s[ci];
+            const float du = d * to_f(d_wout[o]) - u * d3dot;   // dL/du
+            d_w[(size_t)co * n + ci * kk + t] = du * scale * s[ci];
+            ds += du * scale * wv;
+        }
+        atomicAdd(&d_s[ci], ds);
+    }
+}
+
+inline int grid_for(int64_t total, int block = 256) { return (int)((total + block - 1) / block); }
+
+}  // namespace agr
+
+using namespace agr;
+
+extern "C" {
+
+int agr_upfirdn2d(int32_t dtype, const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t out_h,
+                  int32_t out_w, const float* taps, int32_t kh, int32_t kw, int32_t up, int32_t down, int32_t pad_x0,
+                  int32_t pad_y0, void* cuda_stream) {
+    if (!x || !y || !taps || kh < 1 || kw < 1 || kh * kw > 64 || up < 1 || down < 1 || N < 1 || C < 1) return AGR_ERR_INVALID_ARGUMENT;
+    if (out_h < 1 || out_w < 1) return AGR_OK;
+    FirParams fp;
+    for (int i = 0; i < kh * kw; ++i) fp.taps[i] = taps[i];
+    fp.kh = kh; fp.kw = kw; fp.up = up; fp.down = down; fp.pad_x0 = pad_x0; fp.pad_y0 = pad_y0;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    if (dtype == AGR_BF16) {
+        using T = __nv_bfloat16;
+        if (C % 8 == 0) upfirdn_kernel<T, true><<<grid_for((int64_t)N * out_h * out_w * (C / 8)), 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C, out_h, out_w, fp);
+        else upfirdn_kernel<T, false><<<grid_for((int64_t)N * out_h * out_w * C), 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C, out_h, out_w, fp);
+    } else {
+        if (C % 4 == 0) upfirdn_kernel<float, true><<<grid_for((int64_t)N * out_h * out_w * (C / 4)), 256, 0, s>>>((const float*)x, (float*)y, N, H, W, C, out_h, out_w, fp);
+        else upfirdn_kernel<float, false><<<grid_for((int64_t)N * out_h * out_w * C), 256, 0, s>>>((const float*)x, (float*)y, N, H, W, C, out_h, out_w, fp);
+    }
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_haar(int32_t dtype, int32_t mode, const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* cuda_stream) {
+    if (!x || !y || mode < 0 || mode > 3 || N < 1) return AGR_ERR_INVALID_ARGUMENT;
+    const bool analysis = (mode == 0 || mode == 3);
+    if (analysis && ((H & 1) || (W & 1))) return AGR_ERR_INVALID_ARGUMENT;
+    if (!analysis && (C % 4)) return AGR_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const int Ci = analysis ? C : C / 4;
+    const int Hs = analysis ? H / 2 : H, Ws = analysis ? W / 2 : W;
+#define AGR_HAAR(T, VN)                                                                                                 \
+    do {                                                                                                                \
+        if (Ci % VN == 0) {                                                                                             \
+            const int g = grid_for((int64_t)N * Hs * Ws * (Ci / VN));                                                   \
+            if (analysis) haar_kernel<T, true, true><<<g, 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C);                 \
+            else haar_kernel<T, true, false><<<g, 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C);                         \
+        } else {                                                                                                        \
+            const int g = grid_for((int64_t)N * Hs * Ws * Ci);                                                          \
+            if (analysis) haar_kernel<T, false, true><<<g, 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C);                \
+            else haar_kernel<T, false, false><<<g, 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C);                        \
+        }                                                                                                               \
+    } while (0)
+    if (dtype == AGR_BF16) AGR_HAAR(__nv_bfloat16, 8); else AGR_HAAR(float, 4);
+#undef AGR_HAAR
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_bias_act_forward(int32_t dtype, const void* x, void* y, int64_t pixels, int32_t C, const float* bias, const float* noise,
+                         const float* noise_w, int32_t activate, void* cuda_stream) {
+    if (!x || !y || pixels < 0 || C < 1) return AGR_ERR_INVALID_ARGUMENT;
+    if (pixels == 0) return AGR_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const int VN = dtype == AGR_BF16 ? 8 : 4;
+    const bool vec = (C % VN) == 0;
+    const int64_t total = pixels * (vec ? C / VN : C);
+    int g = grid_for(total); if (g > 148 * 32) g = 148 * 32;
+    if (dtype == AGR_BF16) {
+        using T = __nv_bfloat16;
+        if (vec) bias_act_fwd_kernel<T, true><<<g, 256, 0, s>>>((const T*)x, (T*)y, pixels, C, bias, noise, noise_w, activate);
+        else bias_act_fwd_kernel<T, false><<<g, 256, 0, s>>>((const T*)x, (T*)y, pixels, C, bias, noise, noise_w, activate);
+    } else {
+        if (vec) bias_act_fwd_kernel<float, true><<<g, 256, 0, s>>>((const float*)x, (float*)y, pixels, C, bias, noise, noise_w, activate);
+        else bias_act_fwd_kernel<float, false><<<g, 256, 0, s>>>((const float*)x, (float*)y, pixels, C, bias, noise, noise_w, activate);
+    }
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx, int64_t pixels, int32_t C, const float* noise,
+                          float* d_bias, float* d_noise_w, int32_t activate, void* cuda_stream) {
+    if (!dy || !dx || (activate && !y) || pixels < 0 || C < 1) return AGR_ERR_INVALID_ARGUMENT;
+    if (pixels == 0) return AGR_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const int VN = dtype == AGR_BF16 ? 8 : 4;
+    const bool vec = (C % VN) == 0;
+    const int cv = vec ? C / VN : C;
+    if (cv > 256) return AGR_ERR_INVALID_ARGUMENT;  // up to 2048 bf16 / 1024 fp32 channels
+    const int lanes = 256 / cv;
+    int ppb = lanes * 16;  // pixels per block
+    int64_t blocks = (pixels + ppb - 1) / ppb;
+    if (blocks > 148 * 16) { blocks = 148 * 16; ppb = (int)((pixels + blocks - 1) / blocks); }
+    const size_t smem = (size_t)(C + 1) * sizeof(float);
+    if (dtype == AGR_BF16) {
+        using T = __nv_bfloat16;
+        if (vec) bias_act_bwd_kernel<T, true><<<(unsigned)blocks, 256, smem, s>>>((const T*)dy, (const T*)y, (T*)dx, pixels, C, noise, d_bias, d_noise_w, activate, ppb);
+        else bias_act_bwd_kernel<T, false><<<(unsigned)blocks, 256, smem, s>>>((const T*)dy, (const T*)y, (T*)dx, pixels, C, noise, d_bias, d_noise_w, activate, ppb);
+    } else {
+        if (vec) bias_act_bwd_kernel<float, true><<<(unsigned)blocks, 256, smem, s>>>((const float*)dy, (const float*)y, (float*)dx, pixels, C, noise, d_bias, d_noise_w, activate, ppb);
+        else bias_act_bwd_kernel<float, false><<<(unsigned)blocks, 256, smem, s>>>((const float*)dy, (const float*)y, (float*)dx, pixels, C, noise, d_bias, d_noise_w, activate, ppb);
+    }
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_modweight_forward(int32_t dtype, const float* w, const float* s, float scale, int32_t Cout, int32_t Cin, int32_t k,
+                          int32_t demodulate, int32_t transpose_io, void* w_out, float* demod_out, void* cuda_stream) {
+    if (!w || !s || !w_out || Cout < 1 || Cin < 1 || k < 1) return AGR_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (dtype == AGR_BF16) modweight_fwd_kernel<__nv_bfloat16><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (__nv_bfloat16*)w_out, demod_out);
+    else modweight_fwd_kernel<float><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (float*)w_out, demod_out);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_modweight_backward(int32_t dtype, const float* w, const float* s, float scale, int32_t Cout, int32_t Cin, int32_t k,
+                           int32_t demodulate, int32_t transpose_io, const void* d_wout, const float* demod, float* d_w,
+                           float* d_s, void* cuda_stream) {
+    if (!w || !s || !d_wout || !d_w || !d_s || (demodulate && !demod)) return AGR_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (dtype == AGR_BF16) modweight_bwd_kernel<__nv_bfloat16><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const __nv_bfloat16*)d_wout, demod, d_w, d_s);
+    else modweight_bwd_kernel<float><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const float*)d_wout, demod, d_w, d_s);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+}  // extern "C"

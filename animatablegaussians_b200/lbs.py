@@ -4,7 +4,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, stats
 
 _p = C.c_void_p
 _lib.register_symbols({
@@ -41,7 +41,7 @@ class _LBS(torch.autograd.Function):
         qo = torch.empty_like(q)
         need_bwd = positions.requires_grad or rotations.requires_grad
         pt = torch.empty((N, 12), dtype=torch.float32, device=dev) if need_bwd else None
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), stats.stage("lbs", launches=1):
             _check(lib.agr_lbs_forward(N, J, _ptr(w), _ptr(A), _ptr(x), _ptr(q), _ptr(xo), _ptr(qo), _ptr(pt), _stream(dev)),
                    "agr_lbs_forward")
         if need_bwd:
@@ -58,7 +58,7 @@ class _LBS(torch.autograd.Function):
         gq = torch.zeros((N, 4), dtype=torch.float32, device=dev) if gq is None else gq.float().contiguous()
         dx = torch.empty((N, 3), dtype=torch.float32, device=dev)
         dq = torch.empty((N, 4), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), stats.stage("lbs", launches=1):
             _check(lib.agr_lbs_backward(N, _ptr(pt), _ptr(q), _ptr(gx), _ptr(gq), _ptr(dx), _ptr(dq), _stream(dev)),
                    "agr_lbs_backward")
         return None, None, dx, dq
@@ -80,6 +80,6 @@ def skin_points(lbs_weights, jnt_mats, points, normals=None):
     v = normals.detach().float().contiguous() if normals is not None else None
     xo = torch.empty_like(x)
     vo = torch.empty_like(v) if v is not None else None
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), stats.stage("lbs", launches=1):
         _check(lib.agr_lbs_points(N, J, _ptr(w), _ptr(A), _ptr(x), _ptr(v), _ptr(xo), _ptr(vo), _stream(dev)), "agr_lbs_points")
     return xo if normals is None else (xo, vo)

@@ -1,0 +1,58 @@
+"""Flat-bucket Adam: all trainable parameters of the avatar live in ONE fp32 buffer (and their gradients in
+another), so that (a) the view-sharded step needs exactly one NCCL all-reduce and (b) the optimizer is one
+fused streaming kernel (include/agr_optim.h).  Mirrors torch.optim.Adam(lr) + step() + zero_grad() of the
+reference trainer (main_avatar.py:49-51,255-256)."""
+import ctypes as C
+
+import torch
+
+from . import _lib, stats
+
+_p = C.c_void_p
+_lib.register_symbols({
+    "agr_adam_step": (C.c_int, [C.c_int64, _p, _p, _p, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                C.c_float, C.c_int32, _p]),
+})
+
+
+class FlatAdam:
+    def __init__(self, params, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        # pad each tensor to a multiple of 4 elements so every view is 16-byte aligned
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.numel = n
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, offs):
+            k = p.numel()
+            self.flat_param[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[o:o + k].view_as(p.data)
+            p.grad = self.flat_grad[o:o + k].view_as(p.data)
+        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+
+    def all_reduce(self, group=None):
+        """The ONE collective of the view-sharded step: sum of the flat gradient bucket."""
+        import torch.distributed as dist
+        dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
+
+    def step(self, grad_scale=1.0, zero_grad=True):
+        lib = _lib.load()
+        self.t += 1
+        dev = self.flat_param.device
+        with torch.cuda.device(dev), stats.stage("adam", launches=1):
+            st = lib.agr_adam_step(self.flat_param.numel(), C.c_void_p(self.flat_param.data_ptr()),
+                                   C.c_void_p(self.flat_grad.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
+                                   C.c_void_p(self.exp_avg_sq.data_ptr()), self.lr, self.betas[0], self.betas[1], self.eps,
+                                   self.t, grad_scale, int(zero_grad), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        if st != _lib.AGR_OK:
+            raise RuntimeError("agr_adam_step failed: %d" % st)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()

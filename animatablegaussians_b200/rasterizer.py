@@ -15,7 +15,7 @@ from typing import NamedTuple, Optional, Sequence
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, stats
 
 _EMPTY = None
 
@@ -167,8 +167,12 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
             a.binning_ws, a.binning_bytes = _ptr(binning), ws.binning_bytes
             a.capacity = capacity
             a.num_rendered = C.pointer(num_rendered)
-            st = lib.agr_raster_forward(C.byref(a), stream)
+            with stats.stage("raster_fwd", launches=4):
+                st = lib.agr_raster_forward(C.byref(a), stream)
             if st == _lib.AGR_ERR_BINNING_CAPACITY:
+                if num_rendered.value >= (1 << 31):
+                    raise RuntimeError("rasterizer: %d (tile, Gaussian) instances — degenerate input (screen-filling "
+                                       "Gaussians); refusing to allocate the binning workspace" % num_rendered.value)
                 capacity = int(num_rendered.value * 1.25) + 1024
                 continue
             break
@@ -241,7 +245,7 @@ def _backward_impl(saved_tensors, meta, grad_color, grad_depth, grad_alpha):
     a.binning_ws, a.binning_bytes = _ptr(binning), bb
     a.backward_ws, a.backward_bytes = _ptr(bwd_ws), bwb
     a.capacity, a.num_rendered = meta["capacity"], meta["R"]
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), stats.stage("raster_bwd", launches=2):
         st = lib.agr_raster_backward(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     if st != _lib.AGR_OK:
         _raise_status(st, "agr_raster_backward")

@@ -1,0 +1,70 @@
+"""Launch counting and per-stage device timing (CUDA events on the launching stream) for bench.py.
+
+The roofline numbers bench.py prints come from here:
+  raster   : HBM-bound.  Algorithmic bytes per view (SURVEY.md §8d / BASELINE.md §3):
+             B_raster = 184*P + 52*W*H   (fwd: 56 B/Gaussian in + 4 B radii + 24 B/pixel out;
+                                          bwd: 56 B re-read + 28 B/pixel in + 68 B/Gaussian gradients out)
+  lbs      : HBM-bound.  580*N bytes per pose fwd+bwd (276*N fwd, 304*N bwd).
+  styleunet: tensor-bound. Dense-conv FLOPs with the exact per-pose prefix cache:
+             3 * (3*585.8 + (v-1)*136.0) GFLOP for v local views (fwd + 2x bwd).
+"""
+import contextlib
+
+import torch
+
+ENABLED = False
+_events = {}
+_launches = 0
+
+
+def reset():
+    global ENABLED, _events, _launches
+    ENABLED, _events, _launches = True, {}, 0
+
+
+def count(n):
+    global _launches
+    if ENABLED:
+        _launches += n
+
+
+@contextlib.contextmanager
+def stage(name, launches=0):
+    """Times the enclosed C-ABI call(s) with CUDA events on the current stream; `launches` = number of OUR
+    kernels the call launches (library kernels such as CUB / cuDNN are not counted)."""
+    if not ENABLED:
+        yield
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    yield
+    e1.record()
+    _events.setdefault(name, []).append((e0, e1))
+    count(launches)
+
+
+def snapshot():
+    global ENABLED
+    torch.cuda.synchronize()
+    out = {"launches": _launches, "stages": {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in _events.items()}}
+    ENABLED = False
+    return out
+
+
+def stage_ms(st, steps):
+    return {k: round(ms / steps, 4) for k, (ms, n) in st["stages"].items()}
+
+
+def roofline(st, steps, views_local, P, W, H, peaks):
+    hbm = peaks.get("hbm_gbs")
+    which = "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
+    if not hbm:
+        hbm, which = 6650.0, "fallback (B200_PROFILING.md)"
+    s = st["stages"]
+    t_raster = (s.get("raster_fwd", (0, 0))[0] + s.get("raster_bwd", (0, 0))[0]) / steps * 1e-3
+    bytes_step = (184.0 * P + 52.0 * W * H) * views_local
+    achieved = bytes_step / t_raster / 1e9 if t_raster > 0 else 0.0
+    return {"bound": "hbm", "kernel": "rasterizer fwd+bwd launches of one step (preprocess, duplicate, CUB scan/sort, "
+            "gather, blend fwd, blend bwd, preprocess bwd)", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+            "frac": achieved / hbm, "traffic": None, "peak_source": which,
+            "algorithmic_bytes_per_step": bytes_step, "seconds_per_step": t_raster}

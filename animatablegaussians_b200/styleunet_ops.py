@@ -1,9 +1,10 @@
-"""Operators of the B200 DualStyleUNet (see styleunet.py).
+"""Operators of the B200 DualStyleUNet (see styleunet.py): autograd wrappers around the sm_100a kernels of
+include/agr_styleunet.h.  Activations are NHWC (torch channels_last), fp32 (parity tests) or bf16.
 
-Every operator has ONE implementation.  Operators whose hand-written sm_100a kernel exists call it through
-the C ABI (include/agr_styleunet.h); operators listed in LIBRARY_OPS below still call a vendor library
-(cuDNN through torch) and are reported as such by bench.py — they are the next kernels to replace, not a
-fallback: there is no runtime switch between a kernel and a library path.
+Every operator has ONE implementation and no CPU / PyTorch fallback.  The dense contractions listed in
+LIBRARY_OPS are still vendor-library calls (cuDNN through torch) in this round and are reported as such by
+bench.py; everything around them (weight modulation/demodulation, noise + bias + activation, FIR resampling,
+Haar transforms) is hand-written CUDA.
 
 Semantics restated from the reference:
   bias_act            network/styleunet/fused_act.py:100-132, fused_bias_act_kernel.cu:18-65 (act=3)
@@ -12,16 +13,29 @@ Semantics restated from the reference:
   modulated_conv2d    dual_styleunet.py:225-300 (fused branch) + :303-313 (noise) + fused lrelu
   equal_conv2d        dual_styleunet.py:93-122 + ConvLayer :329-371
 """
+import ctypes as C
 import math
 
 import torch
 import torch.nn.functional as F
 
-# operators that are still vendor-library calls (cuDNN via torch) in this round
-LIBRARY_OPS = ("conv2d(cuDNN)", "conv_transpose2d(cuDNN)")
+from . import _lib, stats
+
+LIBRARY_OPS = ("conv2d fwd/dgrad/wgrad (cuDNN via torch)", "conv_transpose2d fwd/dgrad/wgrad (cuDNN via torch)",
+               "viewdir_net 4x4 convs (cuDNN via torch)", "bilinear resize of the view feature (ATen)")
+
+_p = C.c_void_p
+_lib.register_symbols({
+    "agr_upfirdn2d": (C.c_int, [C.c_int32, _p, _p] + [C.c_int32] * 6 + [C.POINTER(C.c_float)] + [C.c_int32] * 6 + [_p]),
+    "agr_haar": (C.c_int, [C.c_int32, C.c_int32, _p, _p] + [C.c_int32] * 4 + [_p]),
+    "agr_bias_act_forward": (C.c_int, [C.c_int32, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int32, _p]),
+    "agr_bias_act_backward": (C.c_int, [C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int32, _p]),
+    "agr_modweight_forward": (C.c_int, [C.c_int32, _p, _p, C.c_float] + [C.c_int32] * 5 + [_p, _p, _p]),
+    "agr_modweight_backward": (C.c_int, [C.c_int32, _p, _p, C.c_float] + [C.c_int32] * 5 + [_p, _p, _p, _p, _p]),
+})
 
 _COMPUTE_DTYPE = torch.float32
-_SQRT2 = math.sqrt(2.0)
+_CL = torch.channels_last
 
 
 def set_compute_dtype(dtype):
@@ -36,122 +50,248 @@ def compute_dtype():
 
 
 def to_compute(x):
-    x = x.to(_COMPUTE_DTYPE)
-    if x.is_cuda and x.ndim == 4:
-        x = x.contiguous(memory_format=torch.channels_last)
-    return x
+    return x.to(_COMPUTE_DTYPE).contiguous(memory_format=_CL)
 
 
 def from_compute(x):
     return x.float().contiguous()
 
 
-def _w(t):
-    return t.to(_COMPUTE_DTYPE)
+def _code(t):
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float32:
+        return 0
+    raise TypeError("StyleUNet kernels take fp32 or bf16 activations, got %s" % t.dtype)
 
 
-# ------------------------------------------------------------------------------------------ elementwise
-def bias_act(x, bias=None, noise=None, noise_weight=None, activate=True):
-    """y = lrelu(x + w_noise * noise + bias[c], 0.2) * sqrt(2)   (activate=False: no lrelu / gain)."""
-    if noise is not None:
-        x = x + _w(noise_weight) * _w(noise)
-    if bias is not None:
-        x = x + _w(bias).view(1, -1, *([1] * (x.ndim - 2)))
-    if activate:
-        x = F.leaky_relu(x, 0.2) * _SQRT2
-    return x
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def bilinear_resize(x, size):
-    """F.interpolate(mode='bilinear') of the view feature (dual_styleunet.py:882,901)."""
-    return F.interpolate(x.float(), size, mode="bilinear").to(_COMPUTE_DTYPE)
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _check(st, what):
+    if st != _lib.AGR_OK:
+        raise RuntimeError("%s failed (status %d) %s" % (what, st, _lib.cuda_error_string() if st == _lib.AGR_ERR_CUDA else ""))
+
+
+def _nhwc(x):
+    if not x.is_cuda:
+        raise RuntimeError("animatablegaussians_b200 StyleUNet operators are CUDA-only (no CPU fallback)")
+    return x.contiguous(memory_format=_CL)
+
+
+def _new_like(x, C_, H, W):
+    return torch.empty((x.shape[0], C_, H, W), dtype=x.dtype, device=x.device, memory_format=_CL)
 
 
 # ------------------------------------------------------------------------------------------ FIR resampling
+_taps_cache = {}
+
+
+def _host_taps(kernel, flip):
+    """(kh,kw) device buffer -> ctypes float array (flipped or not); cached, one D2H per distinct kernel."""
+    key = (kernel.data_ptr(), tuple(kernel.shape), flip, kernel._version)
+    hit = _taps_cache.get(key)
+    if hit is None:
+        k = kernel.detach().float().cpu()
+        if flip:
+            k = torch.flip(k, [0, 1])
+        vals = [float(v) for v in k.reshape(-1)]
+        hit = ((C.c_float * len(vals))(*vals), int(k.shape[0]), int(k.shape[1]))
+        _taps_cache[key] = hit
+    return hit
+
+
+def _fir_launch(x, taps, kh, kw, up, down, px0, py0, out_h, out_w):
+    lib = _lib.load()
+    y = _new_like(x, x.shape[1], out_h, out_w)
+    with torch.cuda.device(x.device), stats.stage("styleunet_fir", launches=1):
+        _check(lib.agr_upfirdn2d(_code(x), _ptr(x), _ptr(y), x.shape[0], x.shape[2], x.shape[3], x.shape[1], out_h, out_w,
+                                 C.cast(taps, C.POINTER(C.c_float)), kh, kw, up, down, px0, py0, _stream(x)), "agr_upfirdn2d")
+    return y
+
+
+class _UpFirDn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, up, down, pad):
+        x = _nhwc(x)
+        px0, px1, py0, py1 = pad
+        kh, kw = kernel.shape
+        H, W = x.shape[2], x.shape[3]
+        out_h = (H * up + py0 + py1 - kh + down) // down
+        out_w = (W * up + px0 + px1 - kw + down) // down
+        taps, _, _ = _host_taps(kernel, True)
+        ctx.kernel, ctx.cfg = kernel, (up, down, px0, py0, kh, kw, H, W)
+        return _fir_launch(x, taps, kh, kw, up, down, px0, py0, out_h, out_w)
+
+    @staticmethod
+    def backward(ctx, g):
+        up, down, px0, py0, kh, kw, H, W = ctx.cfg
+        taps, _, _ = _host_taps(ctx.kernel, False)  # adjoint: correlate with the un-flipped kernel
+        gx = _fir_launch(_nhwc(g), taps, kh, kw, down, up, kw - px0 - 1, kh - py0 - 1, H, W)
+        return gx, None, None, None, None
+
+
 def upfirdn2d(x, kernel, up=1, down=1, pad=(0, 0)):
-    """Per-channel: zero-insert upsample by `up`, pad, convolve with `kernel` (true convolution), decimate."""
     if len(pad) == 2:
         pad = (pad[0], pad[1], pad[0], pad[1])
-    px0, px1, py0, py1 = pad
-    B, C, H, W = x.shape
-    kh, kw = kernel.shape
-    y = x.reshape(B * C, 1, H, W)
-    if up > 1:
-        z = y.new_zeros(B * C, 1, H, up, W, up)
-        z[:, :, :, 0, :, 0] = y
-        y = z.reshape(B * C, 1, H * up, W * up)
-    y = F.pad(y, [max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)])
-    y = y[:, :, max(-py0, 0): y.shape[2] - max(-py1, 0), max(-px0, 0): y.shape[3] - max(-px1, 0)]
-    w = torch.flip(kernel, [0, 1]).view(1, 1, kh, kw).to(y.dtype)
-    y = F.conv2d(y, w, stride=down)
-    return y.reshape(B, C, y.shape[2], y.shape[3])
+    return _UpFirDn.apply(x, kernel, up, down, tuple(int(p) for p in pad))
 
 
-def _haar_kernels(dev, inverse):
-    s = 0.5
-    ll = torch.tensor([[s, s], [s, s]], device=dev)
-    lh = torch.tensor([[-s, -s], [s, s]], device=dev)
-    hl = torch.tensor([[-s, s], [-s, s]], device=dev)
-    hh = torch.tensor([[s, -s], [-s, s]], device=dev)
-    return (ll, -lh, -hl, hh) if inverse else (ll, lh, hl, hh)
+class _Haar(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, analysis):
+        x = _nhwc(x)
+        ctx.analysis = analysis
+        return _Haar._run(x, analysis)
+
+    @staticmethod
+    def _run(x, analysis):
+        lib = _lib.load()
+        B, Cc, H, W = x.shape
+        y = _new_like(x, Cc * 4, H // 2, W // 2) if analysis else _new_like(x, Cc // 4, H * 2, W * 2)
+        with torch.cuda.device(x.device), stats.stage("styleunet_fir", launches=1):
+            _check(lib.agr_haar(_code(x), 0 if analysis else 2, _ptr(x), _ptr(y), B, H, W, Cc, _stream(x)), "agr_haar")
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Haar._run(_nhwc(g), not ctx.analysis), None  # orthonormal: adjoint == inverse
 
 
 def haar_dwt(x):
     """HaarTransform.forward (dual_styleunet.py:398-404): C -> 4C at half resolution, order ll|lh|hl|hh."""
-    ks = _haar_kernels(x.device, False)
-    return torch.cat([upfirdn2d(x, k, down=2) for k in ks], 1)
+    return _Haar.apply(x, True)
 
 
 def haar_iwt(x):
     """InverseHaarTransform.forward (dual_styleunet.py:418-425): 4C -> C at double resolution."""
-    ks = _haar_kernels(x.device, True)
-    parts = x.chunk(4, 1)
-    out = None
-    for p, k in zip(parts, ks):
-        y = upfirdn2d(p, k, up=2, pad=(1, 0, 1, 0))
-        out = y if out is None else out + y
-    return out
+    return _Haar.apply(x, False)
 
 
 def wavelet_upsample(skip, up_kernel):
     """ToRGB skip path (dual_styleunet.py:624-631): dwt(upsample(iwt(skip)))."""
-    k = up_kernel
-    p = k.shape[0] - 2
+    p = up_kernel.shape[0] - 2
     y = haar_iwt(skip)
-    y = upfirdn2d(y, k, up=2, pad=((p + 1) // 2 + 1, p // 2))
+    y = upfirdn2d(y, up_kernel, up=2, pad=((p + 1) // 2 + 1, p // 2))
     return haar_dwt(y)
+
+
+# ------------------------------------------------------------------------------------------ bias + noise + act
+class _BiasAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, noise, noise_weight, activate):
+        lib = _lib.load()
+        is4 = x.ndim == 4
+        x = _nhwc(x) if is4 else x.contiguous()
+        Cc = x.shape[1]
+        pixels = x.numel() // Cc
+        y = torch.empty_like(x)
+        b = bias.detach().float().contiguous() if bias is not None else None
+        nz = noise.detach().float().contiguous() if noise is not None else None
+        nw = noise_weight.detach().float().contiguous() if noise_weight is not None else None
+        if nz is not None and nz.numel() != pixels:
+            raise RuntimeError("noise must have one value per pixel")
+        with torch.cuda.device(x.device), stats.stage("styleunet_act", launches=1):
+            _check(lib.agr_bias_act_forward(_code(x), _ptr(x), _ptr(y), pixels, Cc, _ptr(b), _ptr(nz), _ptr(nw), int(activate),
+                                            _stream(x)), "agr_bias_act_forward")
+        ctx.save_for_backward(y if activate else None, nz)
+        ctx.meta = (activate, is4, bias is not None, noise_weight is not None and noise is not None, Cc, pixels,
+                    None if bias is None else bias.shape, None if noise_weight is None else noise_weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        y, nz = ctx.saved_tensors
+        activate, is4, has_b, has_n, Cc, pixels, bshape, nshape = ctx.meta
+        g = _nhwc(g) if is4 else g.contiguous()
+        dx = torch.empty_like(g)
+        db = torch.zeros(Cc, dtype=torch.float32, device=g.device) if has_b else None
+        dn = torch.zeros(1, dtype=torch.float32, device=g.device) if has_n else None
+        with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
+            _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dx), pixels, Cc, _ptr(nz) if has_n else None,
+                                             _ptr(db), _ptr(dn), int(activate), _stream(g)), "agr_bias_act_backward")
+        return dx, (db.view(bshape) if has_b else None), None, (dn.view(nshape) if has_n else None), None
+
+
+def bias_act(x, bias=None, noise=None, noise_weight=None, activate=True):
+    """y = lrelu(x + w_noise * noise + bias[c], 0.2) * sqrt(2)   (activate=False: no lrelu / gain)."""
+    return _BiasAct.apply(x, bias, noise, noise_weight, activate)
+
+
+def bilinear_resize(x, size):
+    """F.interpolate(mode='bilinear') of the view feature (dual_styleunet.py:882,901)."""
+    return F.interpolate(x.float(), size, mode="bilinear").to(_COMPUTE_DTYPE).contiguous(memory_format=_CL)
+
+
+# ------------------------------------------------------------------------------------------ weight preparation
+class _ModWeight(torch.autograd.Function):
+    """(Cout,Cin,k,k) fp32 master weight + (Cin,) style -> conv-ready weight in the compute dtype, KRSC memory
+    (torch channels_last).  transpose_io -> (Cin,Cout,k,k) operand of conv_transpose2d."""
+
+    @staticmethod
+    def forward(ctx, weight, s, scale, demodulate, transpose_io, dtype):
+        lib = _lib.load()
+        w = weight.detach().float().contiguous()
+        Cout, Cin, k = w.shape[-4], w.shape[-3], w.shape[-1]
+        sv = s.detach().float().contiguous().view(-1)
+        shape = (Cin, Cout, k, k) if transpose_io else (Cout, Cin, k, k)
+        out = torch.empty(shape, dtype=dtype, device=w.device, memory_format=_CL)
+        demod = torch.empty(Cout, dtype=torch.float32, device=w.device) if demodulate else None
+        with torch.cuda.device(w.device), stats.stage("styleunet_weight", launches=1):
+            _check(lib.agr_modweight_forward(_code(out), _ptr(w), _ptr(sv), float(scale), Cout, Cin, k, int(demodulate),
+                                             int(transpose_io), _ptr(out), _ptr(demod), _stream(w)), "agr_modweight_forward")
+        ctx.save_for_backward(w, sv, demod)
+        ctx.meta = (float(scale), Cout, Cin, k, demodulate, transpose_io, weight.shape, s.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        w, sv, demod = ctx.saved_tensors
+        scale, Cout, Cin, k, demodulate, transpose_io, wshape, sshape = ctx.meta
+        g = g.contiguous(memory_format=_CL)
+        dw = torch.empty_like(w)
+        ds = torch.zeros(Cin, dtype=torch.float32, device=w.device)
+        with torch.cuda.device(w.device), stats.stage("styleunet_weight", launches=1):
+            _check(lib.agr_modweight_backward(_code(g), _ptr(w), _ptr(sv), scale, Cout, Cin, k, int(demodulate), int(transpose_io),
+                                              _ptr(g), _ptr(demod), _ptr(dw), _ptr(ds), _stream(w)), "agr_modweight_backward")
+        return dw.view(wshape), ds.view(sshape), None, None, None, None
+
+
+_ones_cache = {}
+
+
+def _ones(n, dev):
+    key = (n, str(dev))
+    if key not in _ones_cache:
+        _ones_cache[key] = torch.ones(n, dtype=torch.float32, device=dev)
+    return _ones_cache[key]
 
 
 # ------------------------------------------------------------------------------------------ dense contractions
 def equal_conv2d(x, weight, scale, stride, padding, act_bias=None, activate=True):
-    out = F.conv2d(x, _w(weight * scale), None, stride=stride, padding=padding)
+    w = _ModWeight.apply(weight, _ones(weight.shape[1], weight.device), scale, False, False, x.dtype)
+    out = F.conv2d(x, w, None, stride=stride, padding=padding)
+    if act_bias is None and not activate:
+        return out
     return bias_act(out, act_bias, activate=activate)
-
-
-def prepare_modulated_weight(weight, s, scale, demodulate):
-    """(1,Cout,Cin,k,k), (B,Cin) -> (B,Cout,Cin,k,k): scale * w * s, optionally demodulated
-    (dual_styleunet.py:256-261)."""
-    B = s.shape[0]
-    w = scale * weight * s.view(B, 1, -1, 1, 1)
-    if demodulate:
-        w = w * torch.rsqrt(w.pow(2).sum([2, 3, 4]) + 1e-8).view(B, -1, 1, 1, 1)
-    return w
 
 
 def modulated_conv2d(x, weight, s, scale, demodulate=True, upsample=False, downsample=False, blur=None, padding=1,
                      noise=None, noise_weight=None, act_bias=None, activate=True):
-    B, Cin, H, W = x.shape
-    Cout, k = weight.shape[1], weight.shape[-1]
-    w = _w(prepare_modulated_weight(weight, s.float(), scale, demodulate))
+    if x.shape[0] != 1:
+        raise RuntimeError("the avatar path runs the StyleUNets at batch 1 (one pose); got batch %d" % x.shape[0])
+    w = _ModWeight.apply(weight, s, scale, demodulate, upsample, x.dtype)
     if upsample:
-        wt = w.transpose(1, 2).reshape(B * Cin, Cout, k, k)
-        out = F.conv_transpose2d(x.reshape(1, B * Cin, H, W), wt, padding=0, stride=2, groups=B)
-        out = blur(out.reshape(B, Cout, out.shape[2], out.shape[3]))
+        out = blur(F.conv_transpose2d(x, w, padding=0, stride=2))
     elif downsample:
-        x = blur(x)
-        out = F.conv2d(x.reshape(1, B * Cin, x.shape[2], x.shape[3]), w.reshape(B * Cout, Cin, k, k), padding=0, stride=2, groups=B)
-        out = out.reshape(B, Cout, out.shape[2], out.shape[3])
+        out = F.conv2d(blur(x), w, padding=0, stride=2)
     else:
-        out = F.conv2d(x.reshape(1, B * Cin, H, W), w.reshape(B * Cout, Cin, k, k), padding=padding, groups=B)
-        out = out.reshape(B, Cout, out.shape[2], out.shape[3])
+        out = F.conv2d(x, w, padding=padding)
     return bias_act(out, act_bias, noise=noise, noise_weight=noise_weight, activate=activate)

@@ -1,0 +1,247 @@
+#!/usr/bin/env python
+"""bench.py — rendered views/sec (fwd+bwd) of the avatar hot path on B200.
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): one training step =
+ONE pose x 16 ring cameras @1024x1024 of a synthetic 300k-Gaussian avatar:
+    3x DualStyleUNet (bf16; position/other nets once, colour net = per-pose prefix + per-view tail)
+    -> gather + activations -> fused LBS -> view-batched rasterizer (RGB+depth+alpha) -> loss
+    -> backward of all of it -> [one NCCL all-reduce of the flat gradient bucket if N>1] -> fused Adam.
+Views are sharded over the N ranks (rank r renders views r, r+N, ...): total work is fixed => "strong".
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value` = views/s with step inputs resident in HBM; `e2e` = same metric
+with the step's inputs coming from pinned HOST buffers (H2D inside the timed region) and the loss read back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+P_GAUSS, IMG, N_VIEWS, J = 300000, 1024, 16, 55
+METRIC = "rendered views/sec fwd+bwd @300k Gaussians, 1024x1024, 16 cams"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ product arm
+class ProductWorkload:
+    def __init__(self, rank, world, device):
+        from animatablegaussians_b200 import avatar, optim, synthetic as S, styleunet_ops as ops
+        self.rank, self.world, self.dev = rank, world, device
+        torch.manual_seed(31359)
+        ops.set_compute_dtype(torch.bfloat16)
+        canonical, jnt_mats = avatar.synthetic_canonical(P_GAUSS, size=IMG, J=J)
+        self.net = avatar.AvatarNet({"with_viewdirs": True}, canonical=canonical, device=device).to(device)
+        self.net.train()
+        self.P = self.net.init_points.shape[0]
+        self.opt = optim.FlatAdam(self.net.parameters(), lr=5e-4)
+        extrs, Ks = S.ring_cameras(N_VIEWS, img=IMG)
+        self.views = list(range(rank, N_VIEWS, world))
+        self.extrs, self.Ks = [extrs[v] for v in self.views], [Ks[v] for v in self.views]
+        # step inputs: host (pinned) master copies + resident device copies
+        self.h_mats = torch.from_numpy(jnt_mats).pin_memory()
+        with torch.no_grad():
+            pose = self.net.get_pose_map({"cano2live_jnt_mats_woRoot": self.h_mats.to(device)})
+            avatar.emulate_pretrained_heads(self.net, pose[:3])
+        self.h_pose = pose.cpu().pin_memory()
+        self.d_mats, self.d_pose = self.h_mats.to(device), self.h_pose.to(device)
+        self.h_loss = torch.zeros(1).pin_memory()
+        self.h2d_bytes = self.h_mats.numel() * 4 + self.h_pose.numel() * 4 + len(self.views) * 35 * 4
+        self.d2h_bytes = 4
+
+    def step(self, e2e):
+        dev = self.dev
+        if e2e:
+            mats = self.h_mats.to(dev, non_blocking=True)
+            pose = self.h_pose.to(dev, non_blocking=True)
+        else:
+            mats, pose = self.d_mats, self.d_pose
+        items = {"smpl_pos_map": pose, "cano2live_jnt_mats": mats}
+        out = self.net.render_views(items, self.extrs, self.Ks, IMG, IMG, bg_color=(0., 0., 0.), return_depth=True)
+        # plain sums so that colour, depth AND alpha receive gradients + offset regulariser
+        loss = (out["rgb_maps"].sum() + out["depth_maps"].sum() + out["mask_maps"].sum()) * (1.0 / (IMG * IMG)) \
+            + 0.005 * torch.linalg.norm(out["offset"], dim=-1).mean()
+        loss.backward()
+        if self.world > 1:
+            self.opt.all_reduce()
+        self.opt.step(grad_scale=1.0, zero_grad=True)
+        if e2e:
+            self.h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+
+
+def device_time_ms(fn, steps, world):
+    """barrier + sync, time `steps` calls with CUDA events on the current stream, sync; max over ranks."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    return float(ms.item())
+
+
+def cpu_baseline_sample(n_views=2):
+    """Oracle ("port") timed on the host cores: raster fwd+bwd + LBS of `n_views` of the 16 views."""
+    from animatablegaussians_b200 import synthetic as S, camera as C
+    from oracle.raster_oracle import RasterOracle
+    from oracle import lbs_oracle
+    g = S.make_gaussians(P_GAUSS)
+    w, mats = S.make_skinning(g["cano"], J=J)
+    extrs, Ks = S.ring_cameras(N_VIEWS, img=IMG)
+    up = (np.ones((3, IMG, IMG), np.float32), np.ones((1, IMG, IMG), np.float32), np.ones((1, IMG, IMG), np.float32))
+    o = RasterOracle()
+    t0 = time.perf_counter()
+    x = torch.from_numpy(g["xyz"]).requires_grad_(True)
+    q = torch.from_numpy(g["rotations"]).requires_grad_(True)
+    px, pq = lbs_oracle.transform_cano2live(torch.from_numpy(w), torch.from_numpy(mats), x, q)
+    (px.sum() + pq.sum()).backward()
+    for v in range(n_views):
+        cb = C.camera_block(extrs[v], Ks[v], IMG, IMG)
+        o.forward(np.zeros(3, np.float32), px.detach().numpy(), g["rgb"], g["opacity"], g["scales"], pq.detach().numpy(), 1.0, None,
+                  cb["viewmatrix"], cb["projmatrix"], cb["tanfovx"], cb["tanfovy"], IMG, IMG)
+        o.backward(*up)
+    dt = time.perf_counter() - t0
+    return {"value": n_views / dt, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d of 16 views: CPU oracle raster fwd+bwd (oracle/raster_oracle.c, OpenMP) + LBS fwd+bwd "
+                      "(oracle/lbs_oracle.py) at 300k/1024^2; StyleUNet NOT included (the reference has no CPU build of "
+                      "its CUDA ops and its Python cannot travel to the GPU box)" % n_views}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        from oracle import reference_arm
+        return reference_arm.main(args, rank, world, local)
+
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    torch.backends.cudnn.benchmark = True
+    from animatablegaussians_b200 import _lib, stats
+
+    wl = ProductWorkload(rank, world, device)
+    for _ in range(args.warmup):
+        wl.step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stats.reset()
+    ms = device_time_ms(lambda: wl.step(False), args.steps, world)
+    st = stats.snapshot()
+    for _ in range(2):
+        wl.step(True)
+    ms_e2e = device_time_ms(lambda: wl.step(True), args.steps, world)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+
+    ms_step = ms / args.steps
+    value = N_VIEWS / (ms_step * 1e-3)
+    e2e_value = N_VIEWS / (ms_e2e / args.steps * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roof = stats.roofline(st, args.steps, len(wl.views), wl.P, IMG, IMG, peaks)
+    out = {
+        "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16 (StyleUNet) + fp32 (LBS, rasterizer)", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[3]: train step fwd+bwd+Adam, synthetic 300k-Gaussian capsule avatar, "
+                               "1 pose x 16 views @1024x1024, bf16 StyleUNet, view-sharded over %d GPU(s)" % world,
+                   "gaussians": wl.P, "views_per_step": N_VIEWS, "views_per_rank": len(wl.views), "image": [IMG, IMG],
+                   "parallelism": "view-shard x%d + 1 all-reduce" % world,
+                   "l2": "step working set (activations, maps, instance streams: several GB) exceeds the 126 MB L2; no explicit flush",
+                   "library_ops": list(__import__("animatablegaussians_b200.styleunet_ops", fromlist=["x"]).LIBRARY_OPS)},
+        "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes},
+        "gpu_launches": st["launches"], "clocks": clocks, "roofline": roof, "stage_ms_per_step": stats.stage_ms(st, args.steps),
+    }
+    if not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline_sample()
+        except Exception as e:  # the oracle is the checker; its absence must not hide the GPU number
+            out["cpu_baseline"] = {"value": None, "unit": "views/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

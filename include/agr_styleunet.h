@@ -1,0 +1,67 @@
+/*
+ * agr_styleunet.h — C ABI of the StyleUNet operators (NHWC activations, fp32 or bf16).
+ *
+ * Replaces the reference's two native modules and the elementwise glue around its cuDNN convolutions:
+ *   module `fused`     : fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ *                        (network/styleunet/fused_bias_act.cpp:18-31, fused_bias_act_kernel.cu:18-107)
+ *   module `upfirdn2d` : upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+ *                        (network/styleunet/upfirdn2d.cpp:17-30, upfirdn2d_kernel.cu:49-369)
+ *   ModulatedConv2d weight preparation (dual_styleunet.py:256-265), NoiseInjection (:303-313),
+ *   HaarTransform / InverseHaarTransform (:387-425).
+ * and holds the dense 3x3 / 1x1 contraction (implicit GEMM on tcgen05) that replaces the cuDNN calls
+ * (conv2d_gradfix.py:34,66).
+ *
+ * dtype: AGR_F32 = 0, AGR_BF16 = 1 (activations; reductions / parameters stay fp32).
+ * Layout: activations are NHWC (torch channels_last), i.e. x[n][h][w][c] contiguous in c.
+ * All pointers are device pointers owned by the caller except where marked HOST. Returns AgrStatus.
+ */
+#ifndef AGR_STYLEUNET_H_
+#define AGR_STYLEUNET_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGR_F32 0
+#define AGR_BF16 1
+
+/* Per-channel FIR resampling: zero-insert upsample by `up`, pad (pad0 before / implied after), correlate with
+ * `taps` (kh*kw HOST floats, ALREADY flipped, i.e. taps = flip(kernel)), decimate by `down`.
+ * out[oy][ox][c] = sum_{ky,kx} taps[ky][kx] * U[oy*down + ky - pad_y0][ox*down + kx - pad_x0][c],
+ * U[uy][ux] = x[uy/up][ux/up] when uy%up == ux%up == 0 and inside, else 0.   kh*kw <= 64. */
+int agr_upfirdn2d(int32_t dtype, const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
+                  int32_t out_h, int32_t out_w, const float* taps, int32_t kh, int32_t kw,
+                  int32_t up, int32_t down, int32_t pad_x0, int32_t pad_y0, void* cuda_stream);
+
+/* Haar analysis (C -> 4C at H/2 x W/2, sub-bands ll|lh|hl|hh) and synthesis (4C -> C at 2H x 2W), and their
+ * adjoints (the backward of one is `transpose` of itself): dual_styleunet.py:387-425.
+ * mode 0: dwt forward, 1: dwt backward (4C,H/2 -> C,H), 2: iwt forward, 3: iwt backward. H, W, C describe x. */
+int agr_haar(int32_t dtype, int32_t mode, const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
+             void* cuda_stream);
+
+/* y = act(x + noise_w[0] * noise[n? no: h][w] + bias[c]),  act = lrelu(.,0.2)*sqrt(2) if activate else identity.
+ * noise: (H,W) fp32 or NULL; noise_w: 1 fp32 on device or NULL; bias: (C) fp32 or NULL. */
+int agr_bias_act_forward(int32_t dtype, const void* x, void* y, int64_t pixels, int32_t C, const float* bias,
+                         const float* noise, const float* noise_w, int32_t activate, void* cuda_stream);
+/* dx = dy * (activate ? (y > 0 ? sqrt2 : 0.2*sqrt2) : 1); d_bias[c] += sum dx; d_noise_w[0] += sum dx*noise.
+ * d_bias / d_noise_w (fp32) are ACCUMULATED into (caller zeroes); either may be NULL. y is the forward OUTPUT. */
+int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx, int64_t pixels, int32_t C,
+                          const float* noise, float* d_bias, float* d_noise_w, int32_t activate, void* cuda_stream);
+
+/* Modulated-convolution weight: w_out[co][ky][kx][ci] (KRSC, dtype) = scale*w[co][ci][ky][kx]*s[ci]*demod[co],
+ * demod[co] = rsqrt(sum_{ci,k} (scale*w*s)^2 + 1e-8) if demodulate else 1.  w fp32 (Cout,Cin,k,k), s fp32 (Cin).
+ * transpose_io != 0 writes w_out[ci][ky][kx][co] instead (operand of the transposed convolution).
+ * demod_out (Cout) fp32 saved for the backward (may be NULL when demodulate == 0). */
+int agr_modweight_forward(int32_t dtype, const float* w, const float* s, float scale, int32_t Cout, int32_t Cin,
+                          int32_t k, int32_t demodulate, int32_t transpose_io, void* w_out, float* demod_out,
+                          void* cuda_stream);
+/* Backward: d_wout (same layout/dtype as w_out) -> d_w (Cout,Cin,k,k) fp32 (overwritten) and d_s (Cin) fp32
+ * (ACCUMULATED; caller zeroes). */
+int agr_modweight_backward(int32_t dtype, const float* w, const float* s, float scale, int32_t Cout, int32_t Cin,
+                           int32_t k, int32_t demodulate, int32_t transpose_io, const void* d_wout,
+                           const float* demod, float* d_w, float* d_s, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

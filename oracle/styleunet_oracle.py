@@ -1,26 +1,155 @@
-"""DualStyleUNet for B200 — host-side mirror of the reference's network/styleunet/dual_styleunet.py
-(`DualStyleUNet`, dual_styleunet.py:636-911) with the same constructor, forward signature and
-state_dict keys/shapes, so the authors' checkpoints load unchanged.
-
-The module tree only *describes* the network (parameters, buffers, wiring).  Arithmetic is delegated to
-animatablegaussians_b200.styleunet_ops, which owns the CUDA kernels:
-    modulated_conv2d / equal_conv2d   dense 3x3 / 1x1 contractions (implicit GEMM)
-    bias_act                          + noise, + bias, leaky-ReLU(0.2) * sqrt(2)     (fused_act.py:100-132)
-    upfirdn2d / haar_dwt / haar_iwt   FIR resampling                                  (upfirdn2d.py:105-183)
-Differences from the reference that do not change results:
-  * modulation, demodulation and the 1/sqrt(fan_in) scale are folded into ONE weight-preparation pass
-    per layer (the reference's `fused` branch materialises the same weight with 5 elementwise launches,
-    dual_styleunet.py:256-265);
-  * noise injection + bias + activation are one epilogue instead of three passes (dual_styleunet.py:598-604);
-  * the shared encoder runs once and the per-view colour decoders can reuse the view-independent prefix
-    (`forward_prefix` / `forward_view_tail`; SURVEY.md §7 hard part (f)).
+"""TEST INFRASTRUCTURE — pure-PyTorch restatement of the reference DualStyleUNet
+(network/styleunet/dual_styleunet.py:13-911, fused_act.py:100-132, upfirdn2d.py:105-227): module tree with the
+reference's state_dict keys + every operator written with plain torch ops (runs on CPU and GPU, any float dtype).
+PINNED: tests/test_styleunet.py checks it against golden vectors produced by the UNMODIFIED reference module
+(tests/golden/make_styleunet_golden.py).  The product (animatablegaussians_b200/styleunet*.py) never imports this
+file; tests use it as the per-operator checker for the CUDA kernels.
 """
 import math
 
 import torch
-from torch import nn
+import torch.nn.functional as F
 
-from . import styleunet_ops as ops
+
+_COMPUTE_DTYPE = torch.float32
+_SQRT2 = math.sqrt(2.0)
+
+
+def set_compute_dtype(dtype):
+    """torch.float32 (parity tests) or torch.bfloat16 (BASELINE config 4: 'bf16 StyleUNet')."""
+    global _COMPUTE_DTYPE
+    assert dtype in (torch.float32, torch.bfloat16)
+    _COMPUTE_DTYPE = dtype
+
+
+def compute_dtype():
+    return _COMPUTE_DTYPE
+
+
+def to_compute(x):
+    x = x.to(_COMPUTE_DTYPE)
+    if x.is_cuda and x.ndim == 4:
+        x = x.contiguous(memory_format=torch.channels_last)
+    return x
+
+
+def from_compute(x):
+    return x.float().contiguous()
+
+
+def _w(t):
+    return t.to(_COMPUTE_DTYPE)
+
+
+# ------------------------------------------------------------------------------------------ elementwise
+def bias_act(x, bias=None, noise=None, noise_weight=None, activate=True):
+    """y = lrelu(x + w_noise * noise + bias[c], 0.2) * sqrt(2)   (activate=False: no lrelu / gain)."""
+    if noise is not None:
+        x = x + noise_weight.to(x.dtype) * noise.to(x.dtype)
+    if bias is not None:
+        x = x + bias.to(x.dtype).view(1, -1, *([1] * (x.ndim - 2)))
+    if activate:
+        x = F.leaky_relu(x, 0.2) * _SQRT2
+    return x
+
+
+def bilinear_resize(x, size):
+    """F.interpolate(mode='bilinear') of the view feature (dual_styleunet.py:882,901)."""
+    return F.interpolate(x.float(), size, mode="bilinear").to(_COMPUTE_DTYPE)
+
+
+# ------------------------------------------------------------------------------------------ FIR resampling
+def upfirdn2d(x, kernel, up=1, down=1, pad=(0, 0)):
+    """Per-channel: zero-insert upsample by `up`, pad, convolve with `kernel` (true convolution), decimate."""
+    if len(pad) == 2:
+        pad = (pad[0], pad[1], pad[0], pad[1])
+    px0, px1, py0, py1 = pad
+    B, C, H, W = x.shape
+    kh, kw = kernel.shape
+    y = x.reshape(B * C, 1, H, W)
+    if up > 1:
+        z = y.new_zeros(B * C, 1, H, up, W, up)
+        z[:, :, :, 0, :, 0] = y
+        y = z.reshape(B * C, 1, H * up, W * up)
+    y = F.pad(y, [max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)])
+    y = y[:, :, max(-py0, 0): y.shape[2] - max(-py1, 0), max(-px0, 0): y.shape[3] - max(-px1, 0)]
+    w = torch.flip(kernel, [0, 1]).view(1, 1, kh, kw).to(y.dtype)
+    y = F.conv2d(y, w, stride=down)
+    return y.reshape(B, C, y.shape[2], y.shape[3])
+
+
+def _haar_kernels(dev, inverse):
+    s = 0.5
+    ll = torch.tensor([[s, s], [s, s]], device=dev)
+    lh = torch.tensor([[-s, -s], [s, s]], device=dev)
+    hl = torch.tensor([[-s, s], [-s, s]], device=dev)
+    hh = torch.tensor([[s, -s], [-s, s]], device=dev)
+    return (ll, -lh, -hl, hh) if inverse else (ll, lh, hl, hh)
+
+
+def haar_dwt(x):
+    """HaarTransform.forward (dual_styleunet.py:398-404): C -> 4C at half resolution, order ll|lh|hl|hh."""
+    ks = _haar_kernels(x.device, False)
+    return torch.cat([upfirdn2d(x, k, down=2) for k in ks], 1)
+
+
+def haar_iwt(x):
+    """InverseHaarTransform.forward (dual_styleunet.py:418-425): 4C -> C at double resolution."""
+    ks = _haar_kernels(x.device, True)
+    parts = x.chunk(4, 1)
+    out = None
+    for p, k in zip(parts, ks):
+        y = upfirdn2d(p, k, up=2, pad=(1, 0, 1, 0))
+        out = y if out is None else out + y
+    return out
+
+
+def wavelet_upsample(skip, up_kernel):
+    """ToRGB skip path (dual_styleunet.py:624-631): dwt(upsample(iwt(skip)))."""
+    k = up_kernel
+    p = k.shape[0] - 2
+    y = haar_iwt(skip)
+    y = upfirdn2d(y, k, up=2, pad=((p + 1) // 2 + 1, p // 2))
+    return haar_dwt(y)
+
+
+# ------------------------------------------------------------------------------------------ dense contractions
+def equal_conv2d(x, weight, scale, stride, padding, act_bias=None, activate=True):
+    out = F.conv2d(x, _w(weight * scale), None, stride=stride, padding=padding)
+    return bias_act(out, act_bias, activate=activate)
+
+
+def prepare_modulated_weight(weight, s, scale, demodulate):
+    """(1,Cout,Cin,k,k), (B,Cin) -> (B,Cout,Cin,k,k): scale * w * s, optionally demodulated
+    (dual_styleunet.py:256-261)."""
+    B = s.shape[0]
+    w = scale * weight * s.view(B, 1, -1, 1, 1)
+    if demodulate:
+        w = w * torch.rsqrt(w.pow(2).sum([2, 3, 4]) + 1e-8).view(B, -1, 1, 1, 1)
+    return w
+
+
+def modulated_conv2d(x, weight, s, scale, demodulate=True, upsample=False, downsample=False, blur=None, padding=1,
+                     noise=None, noise_weight=None, act_bias=None, activate=True):
+    B, Cin, H, W = x.shape
+    Cout, k = weight.shape[1], weight.shape[-1]
+    w = _w(prepare_modulated_weight(weight, s.float(), scale, demodulate))
+    if upsample:
+        wt = w.transpose(1, 2).reshape(B * Cin, Cout, k, k)
+        out = F.conv_transpose2d(x.reshape(1, B * Cin, H, W), wt, padding=0, stride=2, groups=B)
+        out = blur(out.reshape(B, Cout, out.shape[2], out.shape[3]))
+    elif downsample:
+        x = blur(x)
+        out = F.conv2d(x.reshape(1, B * Cin, x.shape[2], x.shape[3]), w.reshape(B * Cout, Cin, k, k), padding=0, stride=2, groups=B)
+        out = out.reshape(B, Cout, out.shape[2], out.shape[3])
+    else:
+        out = F.conv2d(x.reshape(1, B * Cin, H, W), w.reshape(B * Cout, Cin, k, k), padding=padding, groups=B)
+        out = out.reshape(B, Cout, out.shape[2], out.shape[3])
+    return bias_act(out, act_bias, noise=noise, noise_weight=noise_weight, activate=activate)
+
+
+# ===================================================================== module tree
+from torch import nn  # noqa: E402
 
 _CHANNELS = {4: 512, 8: 512, 16: 512, 32: 512, 64: 512, 128: 256, 256: 128, 512: 64, 1024: 32, 2048: 32, 4096: 32}
 
@@ -41,7 +170,7 @@ class _Fir(nn.Module):
         self.up, self.down, self.pad = up, down, pad
 
     def forward(self, x):
-        return ops.upfirdn2d(x, self.kernel, up=self.up, down=self.down, pad=self.pad)
+        return upfirdn2d(x, self.kernel, up=self.up, down=self.down, pad=self.pad)
 
 
 def Blur(blur_kernel, pad, upsample_factor=1):
@@ -76,7 +205,7 @@ class HaarTransform(nn.Module):
             self.register_buffer(n, k)
 
     def forward(self, x):
-        return ops.haar_dwt(x)
+        return haar_dwt(x)
 
 
 class InverseHaarTransform(nn.Module):
@@ -87,7 +216,7 @@ class InverseHaarTransform(nn.Module):
             self.register_buffer(n, k)
 
     def forward(self, x):
-        return ops.haar_iwt(x)
+        return haar_iwt(x)
 
 
 class PixelNorm(nn.Module):
@@ -107,7 +236,7 @@ class EqualLinear(nn.Module):
     def forward(self, x):
         b = self.bias * self.lr_mul if self.bias is not None else None
         if self.activation:
-            return ops.bias_act(nn.functional.linear(x, self.weight * self.scale), b)
+            return bias_act(nn.functional.linear(x, self.weight * self.scale), b)
         return nn.functional.linear(x, self.weight * self.scale, bias=b)
 
 
@@ -126,7 +255,7 @@ class FusedLeakyReLU(nn.Module):
         self.bias = nn.Parameter(torch.zeros(channel)) if bias else None
 
     def forward(self, x):
-        return ops.bias_act(x, self.bias)
+        return bias_act(x, self.bias)
 
 
 class ConvLayer(nn.Sequential):
@@ -156,8 +285,8 @@ class ConvLayer(nn.Sequential):
             i = 1
         conv = self[i]
         if self.activate:
-            return ops.equal_conv2d(x, conv.weight, conv.scale, conv.stride, conv.padding, act_bias=self[i + 1].bias, activate=True)
-        return ops.equal_conv2d(x, conv.weight, conv.scale, conv.stride, conv.padding, act_bias=conv.bias, activate=False)
+            return equal_conv2d(x, conv.weight, conv.scale, conv.stride, conv.padding, act_bias=self[i + 1].bias, activate=True)
+        return equal_conv2d(x, conv.weight, conv.scale, conv.stride, conv.padding, act_bias=conv.bias, activate=False)
 
 
 class ModulatedConv2d(nn.Module):
@@ -201,7 +330,7 @@ class StyledConv(nn.Module):
         if noise is None:  # randomize_noise=True path of the reference (dual_styleunet.py:309-313)
             h = x.shape[2] * (2 if c.upsample else 1)
             noise = x.new_empty(x.shape[0], 1, h, h).normal_()
-        return ops.modulated_conv2d(x, c.weight, s, c.scale, demodulate=c.demodulate, upsample=c.upsample,
+        return modulated_conv2d(x, c.weight, s, c.scale, demodulate=c.demodulate, upsample=c.upsample,
                                     downsample=c.downsample, blur=getattr(c, "blur", None), padding=c.padding,
                                     noise=noise, noise_weight=self.noise.weight, act_bias=self.activate.bias,
                                     activate=True)
@@ -220,10 +349,10 @@ class ToRGB(nn.Module):
 
     def forward(self, x, style, skip=None):
         c = self.conv
-        out = ops.modulated_conv2d(x, c.weight, c.modulation(style), c.scale, demodulate=False, padding=0,
+        out = modulated_conv2d(x, c.weight, c.modulation(style), c.scale, demodulate=False, padding=0,
                                    act_bias=self.bias.view(-1), activate=False)
         if skip is not None:
-            out = out + ops.wavelet_upsample(skip, self.upsample.kernel)  # dwt(upsample(iwt(skip)))
+            out = out + wavelet_upsample(skip, self.upsample.kernel)  # dwt(upsample(iwt(skip)))
         return out
 
 
@@ -346,7 +475,7 @@ class DualStyleUNet(nn.Module):
             out = convs[i + 1](out, latent[:, i + 1], noise=noise[i + 1])
             skip = to_rgbs[lvl](out, latent[:, i + 2], skip)
             if view_feature is not None and i == self.view_level:
-                out = out + ops.bilinear_resize(view_feature, out.shape[-2:])
+                out = out + bilinear_resize(view_feature, out.shape[-2:])
         if stop is not None:
             return out, skip
         return self.iwt(skip)
@@ -359,11 +488,11 @@ class DualStyleUNet(nn.Module):
         latent = self._latent(styles, input_is_latent, truncation, truncation_latent, inject_index)
         if noise is None:
             noise = [None] * self.num_layers if randomize_noise else [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
-        x = ops.to_compute(condition_img)
+        x = to_compute(condition_img)
         cond_list = self.encode(x)
         image1 = self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, view_feature1)
         image2 = self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, view_feature2)
-        images = ops.from_compute(torch.cat([image1, image2], 1))
+        images = from_compute(torch.cat([image1, image2], 1))
         return (images, latent) if return_latents else (images, None)
 
     # ------------------------------------------------------------------ view-batch split (exact)
@@ -372,7 +501,7 @@ class DualStyleUNet(nn.Module):
         level `view_level` (the addition of the view feature happens at the START of the tail)."""
         latent = self._latent(styles, False, 1, None, None)
         noise = [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
-        cond_list = self.encode(ops.to_compute(condition_img))
+        cond_list = self.encode(to_compute(condition_img))
         stop = self.view_level + 2
         s1 = self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, None, stop=stop)
         s2 = self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, None, stop=stop)
@@ -385,7 +514,7 @@ class DualStyleUNet(nn.Module):
                                     (self.convs2, self.to_rgbs2, prefix["s2"], view_feature2)):
             out, skip = st
             if vf is not None and self.view_level < 2 * len(rgbs):  # smaller nets never reach the view level
-                out = out + ops.bilinear_resize(vf, out.shape[-2:])
+                out = out + bilinear_resize(vf, out.shape[-2:])
             outs.append(self._decode(convs, rgbs, prefix["cond_list"], prefix["latent"], prefix["noise"], None,
                                      start=self.view_level + 2, state=(out, skip)))
-        return ops.from_compute(torch.cat(outs, 1))
+        return from_compute(torch.cat(outs, 1))

@@ -12,20 +12,27 @@ from tests.golden import make_styleunet_golden as G
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _build(cfg):
-    from animatablegaussians_b200.styleunet import DualStyleUNet
+def _build(cfg, oracle=False):
+    if oracle:
+        from oracle.styleunet_oracle import DualStyleUNet
+    else:
+        from animatablegaussians_b200.styleunet import DualStyleUNet
     torch.manual_seed(0)
     net = DualStyleUNet(**cfg)
     G.fill_state(net)
     return net
 
 
-def _check(name, device, tol=1e-4):
-    from animatablegaussians_b200 import styleunet_ops as ops
-    ops.set_compute_dtype(torch.float32)
+def _check(name, device, tol=1e-4, oracle=False):
+    if oracle:
+        from oracle import styleunet_oracle as so
+        so.set_compute_dtype(torch.float32)
+    else:
+        from animatablegaussians_b200 import styleunet_ops as ops
+        ops.set_compute_dtype(torch.float32)
     cfg, use_view, stride = G.CASES[name]
     z = np.load(os.path.join(GOLD, "styleunet_%s.npz" % name))
-    net = _build(cfg).to(device)
+    net = _build(cfg, oracle).to(device)
     cond, style, vf1, vf2, up = (t.to(device) if t is not None else None for t in G.inputs(cfg, use_view))
     cond.requires_grad_(True)
     out, _ = net([style], cond, randomize_noise=False, view_feature1=vf1, view_feature2=vf2)
@@ -59,8 +66,15 @@ def test_state_dict_keys_match_reference_listing():
 
 
 @pytest.mark.parametrize("name", ["small", "small8"])
-def test_matches_reference_golden_cpu(name):
-    _check(name, "cpu")
+def test_oracle_matches_reference_golden_cpu(name):
+    """Pins oracle/styleunet_oracle.py (the per-operator checker of the CUDA kernels) to the real reference."""
+    _check(name, "cpu", oracle=True)
+
+
+def test_product_has_no_cpu_path():
+    from animatablegaussians_b200 import styleunet_ops as ops
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        ops.haar_dwt(torch.zeros(1, 4, 8, 8))
 
 
 @pytest.mark.gpu
@@ -84,3 +98,102 @@ def test_prefix_tail_split_is_exact(built_lib):
         pre = net.forward_prefix([style], cond)
         split = net.forward_view_tail(pre, vf1, vf2)
     util.assert_close("split", split.cpu().numpy(), full.cpu().numpy(), 1e-6)
+
+
+# ------------------------------------------------------------------------------------------ per-operator parity
+def _cmp(a, b, tol):
+    util.assert_close("op", a.detach().float().cpu().numpy(), b.detach().float().cpu().numpy(), tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("C,H,W,kind", [(64, 32, 48, "blur1"), (3, 33, 17, "down"), (12, 16, 16, "up"), (128, 9, 9, "blur2"),
+                                         (32, 20, 12, "up"), (8, 15, 15, "blur1")])
+def test_upfirdn2d_matches_oracle(C, H, W, kind, dtype, tol, built_lib):
+    from animatablegaussians_b200 import styleunet_ops as ops
+    from oracle import styleunet_oracle as so
+    k = so.make_kernel([1, 3, 3, 1]).cuda()
+    cfg = {"blur1": dict(kernel=k * 4, up=1, down=1, pad=(1, 1)), "blur2": dict(kernel=k, up=1, down=1, pad=(2, 2)),
+           "up": dict(kernel=k * 4, up=2, down=1, pad=(2, 1)), "down": dict(kernel=k, up=1, down=2, pad=(1, 1))}[kind]
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(1, C, H, W, device="cuda", generator=g)
+    xa = x.to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xb = x.to(dtype).float().requires_grad_(True)
+    ya = ops.upfirdn2d(xa, **cfg)
+    yb = so.upfirdn2d(xb, **cfg)
+    _cmp(ya, yb, tol)
+    up = torch.randn(yb.shape, device="cuda", generator=g)
+    ya.backward(up.to(dtype)); yb.backward(up.to(dtype).float())
+    _cmp(xa.grad, xb.grad, tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("C", [3, 8, 12, 64])
+def test_haar_and_wavelet_upsample_match_oracle(C, dtype, tol, built_lib):
+    from animatablegaussians_b200 import styleunet_ops as ops
+    from oracle import styleunet_oracle as so
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(1, C, 24, 16, device="cuda", generator=g).to(dtype)
+    xa = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xb = x.float().requires_grad_(True)
+    ya, yb = ops.haar_dwt(xa), so.haar_dwt(xb)
+    _cmp(ya, yb, tol)
+    _cmp(ops.haar_iwt(ya), so.haar_iwt(yb), tol)
+    _cmp(ops.haar_iwt(ya), x, 2 * tol)  # orthonormal round trip
+    k = (so.make_kernel([1, 3, 3, 1]) * 4).cuda()
+    if C % 4 == 0:
+        za, zb = ops.wavelet_upsample(xa, k), so.wavelet_upsample(xb, k)
+        _cmp(za, zb, 2 * tol)
+        up = torch.randn(zb.shape, device="cuda", generator=g)
+        za.backward(up.to(dtype)); zb.backward(up.to(dtype).float())
+        _cmp(xa.grad, xb.grad, 3 * tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("C,H,activate,noise", [(512, 16, True, True), (64, 64, True, False), (12, 32, False, False), (3, 8, True, True)])
+def test_bias_act_matches_oracle(C, H, activate, noise, dtype, tol, built_lib):
+    from animatablegaussians_b200 import styleunet_ops as ops
+    from oracle import styleunet_oracle as so
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(1, C, H, H, device="cuda", generator=g).to(dtype)
+    ba, bb = (torch.randn(C, device="cuda", generator=g).requires_grad_(True) for _ in range(2))
+    bb.data.copy_(ba.data)
+    nz = torch.randn(1, 1, H, H, device="cuda", generator=g) if noise else None
+    wa = torch.tensor([0.37], device="cuda", requires_grad=True) if noise else None
+    wb = torch.tensor([0.37], device="cuda", requires_grad=True) if noise else None
+    xa = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xb = x.float().requires_grad_(True)
+    ya = ops.bias_act(xa, ba, nz, wa, activate)
+    yb = so.bias_act(xb, bb, nz, wb, activate)
+    _cmp(ya, yb, tol)
+    up = torch.randn(yb.shape, device="cuda", generator=g)
+    ya.backward(up.to(dtype)); yb.backward(up.to(dtype).float())
+    _cmp(xa.grad, xb.grad, tol)
+    _cmp(ba.grad, bb.grad, 5 * tol)
+    if noise:
+        _cmp(wa.grad, wb.grad, 5 * tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("Cout,Cin,k,demod,tr", [(64, 32, 3, True, False), (12, 64, 1, False, False), (32, 48, 3, True, True), (128, 128, 3, False, False)])
+def test_modweight_matches_oracle(Cout, Cin, k, demod, tr, dtype, tol, built_lib):
+    from animatablegaussians_b200 import styleunet_ops as ops
+    from oracle import styleunet_oracle as so
+    g = torch.Generator(device="cuda").manual_seed(3)
+    w = torch.randn(1, Cout, Cin, k, k, device="cuda", generator=g)
+    s = 1 + 0.3 * torch.randn(1, Cin, device="cuda", generator=g)
+    scale = 1 / (Cin * k * k) ** 0.5
+    wa, sa = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    wb, sb = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    oa = ops._ModWeight.apply(wa, sa, scale, demod, tr, dtype)
+    ob = so.prepare_modulated_weight(wb, sb, scale, demod)[0]
+    if tr:
+        ob = ob.transpose(0, 1)
+    _cmp(oa, ob, tol)
+    up = torch.randn(ob.shape, device="cuda", generator=g)
+    oa.backward(up.to(dtype)); ob.backward(up.to(dtype).float())
+    _cmp(wa.grad, wb.grad, tol)
+    _cmp(sa.grad, sb.grad, 5 * tol)
