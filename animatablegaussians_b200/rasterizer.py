@@ -170,7 +170,7 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
             with stats.stage("raster_fwd", launches=4):
                 st = lib.agr_raster_forward(C.byref(a), stream)
             if st == _lib.AGR_ERR_BINNING_CAPACITY:
-                if num_rendered.value >= (1 << 31):
+                if num_rendered.value >= (1 << 31) or num_rendered.value > 256 * max(P, 1) * V:
                     raise RuntimeError("rasterizer: %d (tile, Gaussian) instances — degenerate input (screen-filling "
                                        "Gaussians); refusing to allocate the binning workspace" % num_rendered.value)
                 capacity = int(num_rendered.value * 1.25) + 1024

@@ -17,3 +17,12 @@ def built_lib():
     """Make sure libagr_b200.so exists (nvcc cross-compiles without a GPU)."""
     from animatablegaussians_b200 import _build
     return _build.build_extension(verbose=False)
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    """fp32 parity tests compare against fp32 references: keep cuDNN / cuBLAS out of TF32."""
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
