@@ -33,7 +33,7 @@ class AgrRasterForwardArgs(C.Structure):
         ("geom_ws", _p), ("geom_bytes", C.c_size_t),
         ("image_ws", _p), ("image_bytes", C.c_size_t),
         ("binning_ws", _p), ("binning_bytes", C.c_size_t),
-        ("capacity", C.c_int64), ("num_rendered", C.POINTER(C.c_int64)),
+        ("capacity", C.c_int64), ("num_rendered", C.POINTER(C.c_int64)), ("device_status", _p),
     ]
 
 

@@ -195,11 +195,12 @@ class AvatarNet(nn.Module):
                                       view_feature1=front_viewdirs, view_feature2=back_viewdirs)
         return self._gather(color_map), self._as_map(color_map)
 
-    def _viewdir_maps(self, items, live_pts, live_nmls):
-        cam_pos = -torch.matmul(torch.linalg.inv(items['extr'][:3, :3]), items['extr'][:3, 3])
+    def _viewdir_maps(self, items, live_pts, live_nmls, cam_pos=None):
+        if cam_pos is None:
+            cam_pos = -torch.matmul(torch.linalg.inv(items['extr'][:3, :3]), items['extr'][:3, 3])
         viewdirs = F.normalize(cam_pos[None] - live_pts, dim=-1, eps=1e-3)
         if self.training:
-            viewdirs += torch.randn(*viewdirs.shape).to(viewdirs) * 0.1
+            viewdirs += torch.randn(viewdirs.shape, dtype=viewdirs.dtype, device=viewdirs.device) * 0.1
         viewdirs = F.normalize(viewdirs, dim=-1, eps=1e-3)
         viewdirs = (live_nmls * viewdirs).sum(-1)
         viewdirs_map = torch.zeros(self.cano_nml_map.shape[0] * self.cano_nml_map.shape[1], dtype=viewdirs.dtype, device=viewdirs.device)
@@ -209,11 +210,11 @@ class AvatarNet(nn.Module):
         half = viewdirs_map.shape[-1] // 2
         return torch.split(viewdirs_map, [half, half], -1)
 
-    def get_viewdir_feat(self, items, live=None):
+    def get_viewdir_feat(self, items, live=None, cam_pos=None):
         with torch.no_grad():
             if live is None:
                 live = lbs.skin_points(self.lbs, items['cano2live_jnt_mats'], self.init_points, self.cano_nmls)
-            front_viewdirs, back_viewdirs = self._viewdir_maps(items, *live)
+            front_viewdirs, back_viewdirs = self._viewdir_maps(items, *live, cam_pos=cam_pos)
         w = self.opt.get('weight_viewdirs', 1.)
         return w * self.viewdir_net(front_viewdirs), w * self.viewdir_net(back_viewdirs)
 
@@ -258,13 +259,26 @@ class AvatarNet(nn.Module):
         return ret
 
     # ------------------------------------------------------------------ view batch (one pose, V cameras)
-    def render_views(self, items, extrs, intrs, img_w, img_h, bg_color=(0., 0., 0.), return_depth=False):
-        """items: pose-level entries ('smpl_pos_map', 'cano2live_jnt_mats'); extrs/intrs: V host (numpy) camera
-        matrices.  Returns rgb_maps (V,H,W,3), mask_maps (V,H,W,1) [, depth_maps (V,H,W,1)], offset, pos_map —
-        per view identical to render() with that camera."""
-        V = len(extrs)
+    def prepare_views(self, extrs, intrs, img_w, img_h, bg_color=(0., 0., 0.), capacity=None):
+        """Host-side camera setup for a view batch (everything render3 derives from extr/intr,
+        gaussian_renderer.py:44-52, plus the camera centres of get_viewdir_feat, avatar.py:131), uploaded with one
+        pinned copy.  `capacity` (tile instances) selects the sync-free rasterizer so that render_views() issues no
+        host synchronisation and can be captured in a CUDA graph."""
         dev = self.device_
-        bg = self._bg(bg_color)
+        bs = camera.make_batched_settings(extrs, intrs, int(img_w), int(img_h), self._bg(bg_color), dev)
+        if capacity is not None:
+            bs = bs._replace(capacity=int(capacity))
+        # cam_pos = -inv(R) t  == camera centre == campos of the raster settings
+        return {"settings": bs, "cam_pos": bs.campos, "V": len(extrs)}
+
+    def render_views(self, items, extrs=None, intrs=None, img_w=None, img_h=None, bg_color=(0., 0., 0.), return_depth=False,
+                     views=None):
+        """items: pose-level entries ('smpl_pos_map', 'cano2live_jnt_mats'); extrs/intrs: V host (numpy) camera
+        matrices, or `views` = prepare_views(...).  Returns rgb_maps (V,H,W,3), mask_maps (V,H,W,1)
+        [, depth_maps (V,H,W,1)], offset, pos_map — per view identical to render() with that camera."""
+        if views is None:
+            views = self.prepare_views(extrs, intrs, img_w, img_h, bg_color)
+        V = views["V"]
         pose_map = items['smpl_pos_map'][:3]
         cano_pts, pos_map = self.get_positions(pose_map, return_map=True)
         opacity, scales, rotations = self.get_others(pose_map)
@@ -275,15 +289,14 @@ class AvatarNet(nn.Module):
             prefix = self.color_net.forward_prefix([self._color_style()], pose_map[None])
             cols = []
             for v in range(V):
-                it = {'extr': torch.as_tensor(np.asarray(extrs[v]), dtype=torch.float32, device=dev)}
-                fv, bv = self.get_viewdir_feat(it, live)
+                fv, bv = self.get_viewdir_feat(None, live, cam_pos=views["cam_pos"][v])
                 cols.append(self._gather(self.color_net.forward_view_tail(prefix, fv, bv)))
             colors = torch.stack(cols, 0)
         else:
             colors, _ = self.get_colors(pose_map)
         pos, rot = lbs.transform_cano2live(self.lbs, items['cano2live_jnt_mats'], cano_pts, rotations)
-        bs = camera.make_batched_settings(extrs, intrs, int(img_w), int(img_h), bg, dev)
-        color, radii, depth, alpha = rasterize_gaussians_batched(pos, None, None, colors, opacity, scales, rot, None, bs)
+        color, radii, depth, alpha = rasterize_gaussians_batched(pos, None, None, colors, opacity, scales, rot, None,
+                                                                 views["settings"])
         ret = {'rgb_maps': color.permute(0, 2, 3, 1), 'mask_maps': alpha.permute(0, 2, 3, 1), 'offset': nonrigid_offset,
                'pos_map': pos_map, 'radii': radii}
         if return_depth:

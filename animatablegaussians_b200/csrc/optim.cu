@@ -5,9 +5,17 @@
 #include <cuda_runtime.h>
 
 namespace agr {
+__global__ void adam_tick_kernel(int32_t* step) { *step += 1; }
+
 __global__ void __launch_bounds__(256) adam_kernel(int64_t n4, int64_t n, float4* __restrict__ p, float4* __restrict__ g,
                                                   float4* __restrict__ m, float4* __restrict__ v, float lr_c, float b1,
-                                                  float b2, float eps, float inv_sqrt_bc2, float gs, int zero) {
+                                                  float b2, float eps, float inv_sqrt_bc2, float gs, int zero,
+                                                  const int32_t* __restrict__ dev_step, float lr) {
+    if (dev_step != nullptr) {  // graph mode: bias corrections from the device-resident step counter
+        const double t = (double)*dev_step;
+        lr_c = (float)((double)lr / (1.0 - pow((double)b1, t)));
+        inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
+    }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 P = p[i], G = g[i], M = m[i], V = v[i];
@@ -57,6 +65,30 @@ extern "C" int agr_adam_step(int64_t n, float* param, float* grad, float* exp_av
     if (blocks < 1) blocks = 1;
     agr::adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
         n4, n, reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(exp_avg),
-        reinterpret_cast<float4*>(exp_avg_sq), lr_c, beta1, beta2, eps, inv_sqrt_bc2, grad_scale, zero_grad);
+        reinterpret_cast<float4*>(exp_avg_sq), lr_c, beta1, beta2, eps, inv_sqrt_bc2, grad_scale, zero_grad, nullptr, lr);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+extern "C" int agr_adam_step_graph(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                                   float beta2, float eps, int32_t* device_step, float grad_scale, int32_t zero_grad,
+                                   void* cuda_stream) {
+    if (n < 0 || !device_step) return AGR_ERR_INVALID_ARGUMENT;
+    if (n == 0) return AGR_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq) return AGR_ERR_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+         reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+        return AGR_ERR_INVALID_ARGUMENT;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    if (blocks < 1) blocks = 1;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    agr::adam_tick_kernel<<<1, 1, 0, s>>>(device_step);
+    agr::adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(
+        n4, n, reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(exp_avg),
+        reinterpret_cast<float4*>(exp_avg_sq), 0.f, beta1, beta2, eps, 0.f, grad_scale, zero_grad, device_step, lr);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }

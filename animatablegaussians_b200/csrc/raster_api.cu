@@ -48,11 +48,13 @@ int agr_raster_forward(const AgrRasterForwardArgs* a, void* cuda_stream) {
     using namespace agr;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     if (!a || a->P < 0 || a->V < 1 || a->V > AGR_MAX_VIEWS || a->width < 1 || a->height < 1) return AGR_ERR_INVALID_ARGUMENT;
-    if (!a->out_color || !a->out_depth || !a->out_alpha || !a->num_rendered) return AGR_ERR_INVALID_ARGUMENT;
+    if (!a->out_color || !a->out_depth || !a->out_alpha) return AGR_ERR_INVALID_ARGUMENT;
+    const bool sync_free = a->num_rendered == nullptr;
+    if (sync_free && a->capacity < 1) return AGR_ERR_INVALID_ARGUMENT;
     const int P = a->P, V = a->V, W = a->width, H = a->height;
     const uint32_t gx = (W + AGR_TILE_X - 1) / AGR_TILE_X, gy = (H + AGR_TILE_Y - 1) / AGR_TILE_Y;
     const uint32_t tiles = gx * gy;
-    *a->num_rendered = 0;
+    if (!sync_free) *a->num_rendered = 0;
     if (P > 0) {
         if (!a->means3D || !a->opacities || !a->radii || !a->viewmatrix || !a->projmatrix || !a->background ||
             !a->tan_fovx || !a->tan_fovy)
@@ -94,12 +96,21 @@ int agr_raster_forward(const AgrRasterForwardArgs* a, void* cuda_stream) {
 
         // number of (tile, Gaussian) instances; the reference does the same blocking read
         // (rasterizer_impl.cu:281-282) to size its binning buffer.
-        uint64_t r64 = 0;
-        if (cuda_fail(cudaMemcpyAsync(&r64, gw.offsets + n - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, s))) return AGR_ERR_CUDA;
-        if (cuda_fail(cudaStreamSynchronize(s))) return AGR_ERR_CUDA;
-        R = (int64_t)r64;
-        *a->num_rendered = R;
-        if (R > a->capacity || R >= ((int64_t)1 << 32)) return AGR_ERR_BINNING_CAPACITY;
+        int64_t* status = a->device_status ? a->device_status : iw.status;
+        if (sync_free) {
+            if (a->capacity >= ((int64_t)1 << 32)) return AGR_ERR_INVALID_ARGUMENT;
+            bw = carve_binning(a->binning_ws, (size_t)a->capacity);
+            launch_finalize_count(gw.offsets + n - 1, (uint64_t)a->capacity, bw.keys_in, status, s);
+            if (stage_fail(debug, s)) return AGR_ERR_CUDA;
+            R = a->capacity;  // launch bound; the real count is read on the device
+        } else {
+            uint64_t r64 = 0;
+            if (cuda_fail(cudaMemcpyAsync(&r64, gw.offsets + n - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, s))) return AGR_ERR_CUDA;
+            if (cuda_fail(cudaStreamSynchronize(s))) return AGR_ERR_CUDA;
+            R = (int64_t)r64;
+            *a->num_rendered = R;
+            if (R > a->capacity || R >= ((int64_t)1 << 32)) return AGR_ERR_BINNING_CAPACITY;
+        }
 
         if (R > 0) {
             bw = carve_binning(a->binning_ws, (size_t)a->capacity);
@@ -116,7 +127,7 @@ int agr_raster_forward(const AgrRasterForwardArgs* a, void* cuda_stream) {
             if (stage_fail(debug, s)) return AGR_ERR_CUDA;
 
             GatherParams gp{};
-            gp.R = (uint32_t)R; gp.P = P; gp.tiles_per_view = tiles;
+            gp.R = (uint32_t)R; gp.P = P; gp.tiles_per_view = tiles; gp.dev_count = sync_free ? status : nullptr;
             gp.keys_sorted = bw.keys_out; gp.vals_sorted = bw.vals_out; gp.ws_rec = gw.rec;
             gp.colors = a->colors_precomp ? a->colors_precomp : gw.rgb;
             gp.colors_view_stride = a->colors_precomp ? (size_t)a->colors_view_stride : (size_t)P * 3;
@@ -157,7 +168,7 @@ int agr_raster_backward(const AgrRasterBackwardArgs* a, void* cuda_stream) {
     float* acc = static_cast<float*>(a->backward_ws);
     if (cuda_fail(cudaMemsetAsync(acc, 0, acc_bytes, s))) return AGR_ERR_CUDA;
 
-    if (a->num_rendered > 0) {
+    if (a->num_rendered != 0) {
         BlendBwdParams bp{};
         bp.W = W; bp.H = H; bp.P = P; bp.grid_x = gx; bp.tiles_per_view = tiles; bp.num_tiles_total = tiles * V;
         bp.ranges = iw.ranges; bp.stream = bw.stream; bp.background = a->background; bp.bg_view_stride = a->bg_view_stride;

@@ -70,6 +70,7 @@ ImageWs carve_image(void* base, size_t V, size_t W, size_t H) {
     take(cur, w.ranges, V * tiles);
     take(cur, w.tile_last, V * tiles);
     take(cur, w.n_contrib, V * W * H);
+    take(cur, w.status, 2);
     w.total = (size_t)(cur - static_cast<char*>(base)) + 128;
     return w;
 }

@@ -178,6 +178,7 @@ struct ImageWs {
     uint2* ranges;         // V*tiles
     uint32_t* n_contrib;   // V*H*W
     uint32_t* tile_last;   // V*tiles: max n_contrib in tile (lets the backward skip the dead tail)
+    int64_t* status;       // 2: instances emitted, overflow flag (sync-free mode)
     size_t total;
 };
 struct BinWs {

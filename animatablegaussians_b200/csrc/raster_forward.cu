@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256) duplicate_kernel(DuplicateParams p) {
 // one-time gather into the tile-major attribute stream.
 __global__ void __launch_bounds__(256) ranges_gather_kernel(GatherParams p) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p.dev_count != nullptr) p.R = (uint32_t)p.dev_count[0];  // sync-free mode
     if (i >= p.R) return;
     const uint64_t key = p.keys_sorted[i];
     const uint32_t tile = (uint32_t)(key >> 32);
@@ -302,6 +303,17 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_fwd_kernel(BlendFwdParams 
     }
 }
 
+// Sync-free mode: publish the instance count on the device, flag overflow, and pad the unused tail of the key
+// buffer with all-ones keys so that sorting `capacity` items leaves the R real instances in front.
+__global__ void __launch_bounds__(256) finalize_count_kernel(const uint64_t* __restrict__ offsets_last, uint64_t capacity,
+                                                            uint64_t* __restrict__ keys, int64_t* __restrict__ status) {
+    const uint64_t total = *offsets_last;
+    const uint64_t R = total < capacity ? total : capacity;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { status[0] = (int64_t)R; status[1] = total > capacity ? 1 : 0; }
+    for (uint64_t i = R + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += (uint64_t)gridDim.x * blockDim.x)
+        keys[i] = ~0ull;
+}
+
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
                                     uint8_t* __restrict__ present) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,6 +330,9 @@ void launch_preprocess_fwd(const PreprocessFwdParams& p, const ViewScalars& vs, 
 void launch_duplicate(const DuplicateParams& p, cudaStream_t s) {
     const size_t n = (size_t)p.V * p.P;
     duplicate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+}
+void launch_finalize_count(const uint64_t* offsets_last, uint64_t capacity, uint64_t* keys, int64_t* status, cudaStream_t s) {
+    finalize_count_kernel<<<148 * 4, 256, 0, s>>>(offsets_last, capacity, keys, status);
 }
 void launch_ranges_gather(const GatherParams& p, cudaStream_t s) {
     if (p.R == 0) return;

@@ -69,6 +69,7 @@ struct DuplicateParams {
 
 struct GatherParams {
     uint32_t R; int P; uint32_t tiles_per_view;
+    const int64_t* dev_count;  // sync-free mode: R lives here (R above = capacity = launch bound)
     const uint64_t* keys_sorted; const uint32_t* vals_sorted;
     const GeomRec* ws_rec;
     const float* colors; size_t colors_view_stride;
@@ -109,6 +110,7 @@ struct PreprocessBwdParams {
 void launch_preprocess_fwd(const PreprocessFwdParams&, const ViewScalars&, cudaStream_t);
 void launch_duplicate(const DuplicateParams&, cudaStream_t);
 void launch_ranges_gather(const GatherParams&, cudaStream_t);
+void launch_finalize_count(const uint64_t* offsets_last, uint64_t capacity, uint64_t* keys, int64_t* status, cudaStream_t);
 void launch_blend_fwd(const BlendFwdParams&, cudaStream_t);
 void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t);
 void launch_blend_bwd(const BlendBwdParams&, cudaStream_t);

@@ -12,6 +12,8 @@ _p = C.c_void_p
 _lib.register_symbols({
     "agr_adam_step": (C.c_int, [C.c_int64, _p, _p, _p, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                 C.c_float, C.c_int32, _p]),
+    "agr_adam_step_graph": (C.c_int, [C.c_int64, _p, _p, _p, _p, C.c_float, C.c_float, C.c_float, C.c_float, _p,
+                                      C.c_float, C.c_int32, _p]),
 })
 
 
@@ -36,16 +38,28 @@ class FlatAdam:
             p.data = self.flat_param[o:o + k].view_as(p.data)
             p.grad = self.flat_grad[o:o + k].view_as(p.data)
         self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        self.device_step = torch.zeros(1, dtype=torch.int32, device=dev)  # used by step(graph_safe=True)
 
     def all_reduce(self, group=None):
         """The ONE collective of the view-sharded step: sum of the flat gradient bucket."""
         import torch.distributed as dist
         dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
 
-    def step(self, grad_scale=1.0, zero_grad=True):
+    def step(self, grad_scale=1.0, zero_grad=True, graph_safe=False):
+        """graph_safe=True keeps the step counter on the device so the call can be captured in a CUDA graph."""
         lib = _lib.load()
-        self.t += 1
         dev = self.flat_param.device
+        if graph_safe:
+            with torch.cuda.device(dev), stats.stage("adam", launches=2):
+                st = lib.agr_adam_step_graph(self.flat_param.numel(), C.c_void_p(self.flat_param.data_ptr()),
+                                             C.c_void_p(self.flat_grad.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
+                                             C.c_void_p(self.exp_avg_sq.data_ptr()), self.lr, self.betas[0], self.betas[1],
+                                             self.eps, C.c_void_p(self.device_step.data_ptr()), grad_scale, int(zero_grad),
+                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if st != _lib.AGR_OK:
+                raise RuntimeError("agr_adam_step_graph failed: %d" % st)
+            return
+        self.t += 1
         with torch.cuda.device(dev), stats.stage("adam", launches=1):
             st = lib.agr_adam_step(self.flat_param.numel(), C.c_void_p(self.flat_param.data_ptr()),
                                    C.c_void_p(self.flat_grad.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),

@@ -71,6 +71,12 @@ class BatchedRasterizationSettings(NamedTuple):
     campos: torch.Tensor
     prefiltered: bool
     debug: bool
+    capacity: Optional[int] = None  # fixed instance capacity -> sync-free (CUDA-graph capturable) forward
+
+
+# device int64[2] = (instances emitted, overflow flag) of the most recent sync-free forward; check it after the
+# graph replay / at the end of the step:  if int(last_device_status[1]): capacity was too small.
+last_device_status = None
 
 
 # capacity (in tile instances) that worked last time for a given problem shape
@@ -134,9 +140,12 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
     radii = torch.empty((V, max(P, 0)), dtype=torch.int32, device=dev)
 
     key = (P, V, H, W)
-    capacity = _capacity_hint.get(key, max(4 * P * V, 1 << 16))
+    fixed_capacity = getattr(rs, "capacity", None)
+    sync_free = fixed_capacity is not None
+    capacity = int(fixed_capacity) if sync_free else _capacity_hint.get(key, max(4 * P * V, 1 << 16))
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     num_rendered = C.c_int64(0)
+    status = torch.empty(2, dtype=torch.int64, device=dev) if sync_free else None
     ws = _lib.AgrRasterWorkspace()
     geom = image = binning = None
     with torch.cuda.device(dev):
@@ -166,7 +175,8 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
             a.image_ws, a.image_bytes = _ptr(image), ws.image_bytes
             a.binning_ws, a.binning_bytes = _ptr(binning), ws.binning_bytes
             a.capacity = capacity
-            a.num_rendered = C.pointer(num_rendered)
+            a.num_rendered = None if sync_free else C.pointer(num_rendered)
+            a.device_status = _ptr(status)
             with stats.stage("raster_fwd", launches=4):
                 st = lib.agr_raster_forward(C.byref(a), stream)
             if st == _lib.AGR_ERR_BINNING_CAPACITY:
@@ -178,8 +188,13 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
             break
         if st != _lib.AGR_OK:
             _raise_status(st, "agr_raster_forward")
-    R = int(num_rendered.value)
-    _capacity_hint[key] = max(int(R * 1.15) + 1024, 1 << 12)
+    if sync_free:
+        global last_device_status
+        last_device_status = status
+        R = -1
+    else:
+        R = int(num_rendered.value)
+        _capacity_hint[key] = max(int(R * 1.15) + 1024, 1 << 12)
 
     saved = _Ctx()
     saved.tensors = (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, image,

@@ -105,27 +105,71 @@ class ProductWorkload:
         self.h_pose = pose.cpu().pin_memory()
         self.d_mats, self.d_pose = self.h_mats.to(device), self.h_pose.to(device)
         self.h_loss = torch.zeros(1).pin_memory()
-        self.h2d_bytes = self.h_mats.numel() * 4 + self.h_pose.numel() * 4 + len(self.views) * 35 * 4
+        # camera block of this rank's views: pinned host master + static device tensors (graph inputs)
+        self.views_dev = self.net.prepare_views(self.extrs, self.Ks, IMG, IMG)
+        st = self.views_dev["settings"]
+        self.h_cam = torch.cat([st.viewmatrix.reshape(len(self.views), 16), st.projmatrix.reshape(len(self.views), 16),
+                                st.campos], 1).cpu().pin_memory()
+        self.h2d_bytes = self.h_mats.numel() * 4 + self.h_pose.numel() * 4 + self.h_cam.numel() * 4
         self.d2h_bytes = 4
+        self.graph = None
 
-    def step(self, e2e):
-        dev = self.dev
-        if e2e:
-            mats = self.h_mats.to(dev, non_blocking=True)
-            pose = self.h_pose.to(dev, non_blocking=True)
-        else:
-            mats, pose = self.d_mats, self.d_pose
-        items = {"smpl_pos_map": pose, "cano2live_jnt_mats": mats}
-        out = self.net.render_views(items, self.extrs, self.Ks, IMG, IMG, bg_color=(0., 0., 0.), return_depth=True)
+    def _body(self):
+        items = {"smpl_pos_map": self.d_pose, "cano2live_jnt_mats": self.d_mats}
+        out = self.net.render_views(items, return_depth=True, views=self.views_dev)
         # plain sums so that colour, depth AND alpha receive gradients + offset regulariser
         loss = (out["rgb_maps"].sum() + out["depth_maps"].sum() + out["mask_maps"].sum()) * (1.0 / (IMG * IMG)) \
             + 0.005 * torch.linalg.norm(out["offset"], dim=-1).mean()
         loss.backward()
         if self.world > 1:
             self.opt.all_reduce()
-        self.opt.step(grad_scale=1.0, zero_grad=True)
+        self.opt.step(grad_scale=1.0, zero_grad=True, graph_safe=True)
+        return loss.detach().reshape(1)
+
+    def capture(self):
+        """Whole train step (3 U-Nets fwd, LBS, raster fwd, loss, full backward, all-reduce, Adam) as ONE CUDA graph:
+        ~9k kernel launches per step replay without per-launch host cost.  Needs the sync-free rasterizer, whose
+        fixed instance capacity is taken from one eager (synchronising) step."""
+        from animatablegaussians_b200 import rasterizer
+        self._body()  # eager: cuDNN autotune, tap caches, and the measured instance count
+        torch.cuda.synchronize()
+        need = max(rasterizer._capacity_hint.values())
+        self.views_dev = dict(self.views_dev, settings=self.views_dev["settings"]._replace(capacity=int(need * 1.2)))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._body()
+        torch.cuda.synchronize()
+
+    def check_overflow(self):
+        from animatablegaussians_b200 import rasterizer
+        st = rasterizer.last_device_status
+        if st is not None and int(st[1].item()) != 0:
+            raise RuntimeError("sync-free rasterizer: binning capacity exceeded (%d instances)" % int(st[0].item()))
+        return None if st is None else int(st[0].item())
+
+    def step(self, e2e):
+        if e2e:  # this step's inputs come from pinned host memory
+            st = self.views_dev["settings"]
+            V = len(self.views)
+            self.d_mats.copy_(self.h_mats, non_blocking=True)
+            self.d_pose.copy_(self.h_pose, non_blocking=True)
+            st.viewmatrix.copy_(self.h_cam[:, :16].reshape(V, 4, 4), non_blocking=True)
+            st.projmatrix.copy_(self.h_cam[:, 16:32].reshape(V, 4, 4), non_blocking=True)
+            st.campos.copy_(self.h_cam[:, 32:35], non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+            loss = self.static_loss
+        else:
+            loss = self._body()
         if e2e:
-            self.h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+            self.h_loss.copy_(loss, non_blocking=True)
         return loss
 
 
@@ -182,6 +226,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -201,6 +246,8 @@ def main():
     from animatablegaussians_b200 import _lib, stats
 
     wl = ProductWorkload(rank, world, device)
+    if not args.no_graph:
+        wl.capture()
     for _ in range(args.warmup):
         wl.step(False)
     sampler = ClockSampler(local)
@@ -210,10 +257,15 @@ def main():
     for _ in range(2):
         wl.step(True)
     ms_e2e = device_time_ms(lambda: wl.step(True), args.steps, world)
-    # per-stage device times + launch count: a separate pass (the event pairs would perturb the timed region)
+    instances = wl.check_overflow()
+    # per-stage device times + launch count: a separate EAGER pass (event pairs cannot be recorded inside a graph
+    # replay and would perturb the timed region anyway)
+    graph, wl.graph = wl.graph, None
+    wl.step(False)
     stats.reset()
     device_time_ms(lambda: wl.step(False), args.steps, world)
     st = stats.snapshot()
+    wl.graph = graph
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         return
@@ -234,7 +286,8 @@ def main():
         "config": {"workload": "BASELINE configs[3]: train step fwd+bwd+Adam, synthetic 300k-Gaussian capsule avatar, "
                                "1 pose x 16 views @1024x1024, bf16 StyleUNet, view-sharded over %d GPU(s)" % world,
                    "gaussians": wl.P, "views_per_step": N_VIEWS, "views_per_rank": len(wl.views), "image": [IMG, IMG],
-                   "parallelism": "view-shard x%d + 1 all-reduce" % world,
+                   "parallelism": "view-shard x%d + 1 all-reduce" % world, "cuda_graph": not args.no_graph,
+                   "tile_instances_per_step": instances,
                    "l2": "step working set (activations, maps, instance streams: several GB) exceeds the 126 MB L2; no explicit flush",
                    "library_ops": list(__import__("animatablegaussians_b200.styleunet_ops", fromlist=["x"]).LIBRARY_OPS)},
         "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes},

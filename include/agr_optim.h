@@ -18,6 +18,12 @@ extern "C" {
 int agr_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                   float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
                   int32_t zero_grad, void* cuda_stream);
+
+/* Same update with the step counter living on the device (int32, incremented by the call itself), so the whole
+ * training step including the optimizer can be captured once in a CUDA graph and replayed. */
+int agr_adam_step_graph(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                        float lr, float beta1, float beta2, float eps, int32_t* device_step, float grad_scale,
+                        int32_t zero_grad, void* cuda_stream);
 #ifdef __cplusplus
 }
 #endif

@@ -99,7 +99,11 @@ typedef struct AgrRasterForwardArgs {
     void* image_ws;   size_t image_bytes;
     void* binning_ws; size_t binning_bytes;
     int64_t capacity;           /* instances the binning workspace was sized for */
-    int64_t* num_rendered;      /* HOST out: instances emitted (reference return value) */
+    int64_t* num_rendered;      /* HOST out: instances emitted (reference return value, costs one stream sync like
+                                 * rasterizer_impl.cu:282).  NULL selects the SYNC-FREE mode: the count stays on the
+                                 * device, nothing blocks (CUDA-graph capturable); `capacity` instances are sorted and
+                                 * an overflow is reported through device_status instead of AGR_ERR_BINNING_CAPACITY. */
+    int64_t* device_status;     /* DEVICE out (2 x int64) or NULL: [0] = instances emitted, [1] = 1 if > capacity */
 } AgrRasterForwardArgs;
 
 int agr_raster_forward(const AgrRasterForwardArgs* args, void* cuda_stream);
@@ -145,7 +149,7 @@ typedef struct AgrRasterBackwardArgs {
     const void* binning_ws; size_t binning_bytes;
     void* backward_ws;      size_t backward_bytes;
     int64_t capacity;
-    int64_t num_rendered;   /* R returned by the forward */
+    int64_t num_rendered;   /* R returned by the forward; pass -1 after a sync-free forward */
 } AgrRasterBackwardArgs;
 
 int agr_raster_backward(const AgrRasterBackwardArgs* args, void* cuda_stream);

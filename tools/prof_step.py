@@ -10,6 +10,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 torch.cuda.set_device(0)
 torch.backends.cudnn.benchmark = True
 wl = bench.ProductWorkload(0, 1, torch.device("cuda", 0))
+if os.environ.get("AGR_GRAPH", "0") == "1":
+    wl.capture()
 for _ in range(warm):
     wl.step(False)
 torch.cuda.synchronize()
