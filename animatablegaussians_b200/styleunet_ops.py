@@ -21,7 +21,9 @@ import torch.nn.functional as F
 
 from . import _lib, stats
 
-LIBRARY_OPS = ("conv2d fwd/dgrad/wgrad (cuDNN via torch)", "conv_transpose2d fwd/dgrad/wgrad (cuDNN via torch)",
+LIBRARY_OPS = ("conv2d wgrad, all shapes (cuDNN via torch)",
+               "conv2d fwd/dgrad for stride-2, 8x8-resolution, Cin=3 and Cout in {12,32} layers (cuDNN via torch)",
+               "conv_transpose2d fwd/dgrad/wgrad (cuDNN via torch)",
                "viewdir_net 4x4 convs (cuDNN via torch)", "bilinear resize of the view feature (ATen)")
 
 _p = C.c_void_p
@@ -32,6 +34,9 @@ _lib.register_symbols({
     "agr_bias_act_backward": (C.c_int, [C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int32, _p]),
     "agr_modweight_forward": (C.c_int, [C.c_int32, _p, _p, C.c_float] + [C.c_int32] * 5 + [_p, _p, _p]),
     "agr_modweight_backward": (C.c_int, [C.c_int32, _p, _p, C.c_float] + [C.c_int32] * 5 + [_p, _p, _p, _p, _p]),
+    "agr_conv2d_tc_supported": (C.c_int, [C.c_int32] * 5),
+    "agr_conv2d_tc_forward": (C.c_int, [_p, _p, _p] + [C.c_int32] * 5 + [_p, _p, _p, C.c_int32, _p]),
+    "agr_weight_flip_transpose": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
 })
 
 _COMPUTE_DTYPE = torch.float32
@@ -275,8 +280,77 @@ def _ones(n, dev):
 
 
 # ------------------------------------------------------------------------------------------ dense contractions
+def _tc_ok(x, Cout, k, stride):
+    if x.dtype != torch.bfloat16 or stride != 1 or x.shape[0] != 1:
+        return False
+    return bool(_lib.load().agr_conv2d_tc_supported(x.shape[2], x.shape[3], x.shape[1], Cout, k))
+
+
+def _tc_conv(x, w, Cout, k, bias, noise, noise_w, activate):
+    """x (1,Cin,H,W) NHWC bf16, w (Cout,Cin,k,k) KRSC bf16 -> (1,Cout,H,W) NHWC bf16 on tcgen05."""
+    lib = _lib.load()
+    y = _new_like(x, Cout, x.shape[2], x.shape[3])
+    with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=1):
+        _check(lib.agr_conv2d_tc_forward(_ptr(x), _ptr(w), _ptr(y), x.shape[2], x.shape[3], x.shape[1], Cout, k, _ptr(bias),
+                                         _ptr(noise), _ptr(noise_w), int(activate), _stream(x)), "agr_conv2d_tc_forward")
+    return y
+
+
+class _ConvAct(torch.autograd.Function):
+    """y = act(conv_same(x, w) + noise_w * noise + bias): forward and data gradient on the tcgen05 implicit-GEMM
+    kernel (epilogue fused), weight gradient still through cuDNN."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, noise, noise_weight, activate):
+        x = _nhwc(x)
+        w = w.contiguous(memory_format=_CL)
+        Cout, k = w.shape[0], w.shape[-1]
+        b = bias.detach().float().contiguous() if bias is not None else None
+        nz = noise.detach().float().contiguous() if noise is not None else None
+        nw = noise_weight.detach().float().contiguous() if noise_weight is not None else None
+        y = _tc_conv(x, w, Cout, k, b, nz, nw if nz is not None else None, activate)
+        ctx.save_for_backward(x, w, y if activate else None, nz)
+        ctx.meta = (activate, k, bias is not None, noise is not None and noise_weight is not None,
+                    None if bias is None else bias.shape, None if noise_weight is None else noise_weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, w, y, nz = ctx.saved_tensors
+        activate, k, has_b, has_n, bshape, nshape = ctx.meta
+        Cout, Cin = w.shape[0], w.shape[1]
+        g = _nhwc(g)
+        pixels = g.shape[2] * g.shape[3]
+        if activate or has_b or has_n:
+            dz = torch.empty_like(g)
+            db = torch.zeros(Cout, dtype=torch.float32, device=g.device) if has_b else None
+            dn = torch.zeros(1, dtype=torch.float32, device=g.device) if has_n else None
+            with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
+                _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dz), pixels, Cout, _ptr(nz) if has_n else None,
+                                                 _ptr(db), _ptr(dn), int(activate), _stream(g)), "agr_bias_act_backward")
+        else:
+            dz, db, dn = g, None, None
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            if lib.agr_conv2d_tc_supported(g.shape[2], g.shape[3], Cout, Cin, k):
+                wt = torch.empty((Cin, Cout, k, k), dtype=w.dtype, device=w.device, memory_format=_CL)
+                with torch.cuda.device(g.device), stats.stage("styleunet_weight", launches=1):
+                    _check(lib.agr_weight_flip_transpose(_ptr(w), _ptr(wt), Cout, Cin, k, _stream(g)), "agr_weight_flip_transpose")
+                dx = _tc_conv(dz, wt, Cin, k, None, None, None, False)
+            else:
+                dx = torch.ops.aten.convolution_backward(dz, x, w, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
+                                                         [True, False, False])[0]
+        if ctx.needs_input_grad[1]:
+            dw = torch.ops.aten.convolution_backward(dz, x, w, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
+                                                     [False, True, False])[1]
+        return dx, dw, (db.view(bshape) if has_b else None), None, (dn.view(nshape) if has_n else None), None
+
+
 def equal_conv2d(x, weight, scale, stride, padding, act_bias=None, activate=True):
     w = _ModWeight.apply(weight, _ones(weight.shape[1], weight.device), scale, False, False, x.dtype)
+    if _tc_ok(x, w.shape[0], w.shape[-1], stride) and padding == w.shape[-1] // 2:
+        return _ConvAct.apply(x, w, act_bias, None, None, activate)
     out = F.conv2d(x, w, None, stride=stride, padding=padding)
     if act_bias is None and not activate:
         return out
@@ -293,5 +367,7 @@ def modulated_conv2d(x, weight, s, scale, demodulate=True, upsample=False, downs
     elif downsample:
         out = F.conv2d(blur(x), w, padding=0, stride=2)
     else:
+        if _tc_ok(x, w.shape[0], w.shape[-1], 1) and padding == w.shape[-1] // 2:
+            return _ConvAct.apply(x, w, act_bias, noise, noise_weight, activate)
         out = F.conv2d(x, w, padding=padding)
     return bias_act(out, act_bias, noise=noise, noise_weight=noise_weight, activate=activate)

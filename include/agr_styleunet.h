@@ -61,6 +61,19 @@ int agr_modweight_backward(int32_t dtype, const float* w, const float* s, float 
                            int32_t k, int32_t demodulate, int32_t transpose_io, const void* d_wout,
                            const float* demod, float* d_w, float* d_s, void* cuda_stream);
 
+/* ---- dense contraction on the tensor cores (tcgen05.mma + TMA, bf16 in / fp32 accumulate / bf16 out) ----
+ * Stride-1 "same" convolution, batch 1, NHWC:  y = act(conv(x, w) + noise_w*noise + bias).
+ *   x (H,W,Cin) bf16, w_krsc (Cout, k, k, Cin) bf16 (what agr_modweight_forward writes), y (H,W,Cout) bf16,
+ *   bias (Cout) fp32 / noise (H,W) fp32 / noise_w (1) fp32 may be NULL; activate: lrelu(0.2)*sqrt(2).
+ * Shapes must satisfy agr_conv2d_tc_supported (H % 8 == 0, W % 16 == 0, Cin % 64 == 0, Cout % 64 == 0, k in {1,3}).
+ * The data gradient of the same convolution is this call on dy with agr_weight_flip_transpose(w). */
+int agr_conv2d_tc_supported(int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);
+int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                          int32_t ksize, const float* bias, const float* noise, const float* noise_w, int32_t activate,
+                          void* cuda_stream);
+/* w_out[ci][k*k-1-t][co] = w_krsc[co][t][ci]  (bf16) */
+int agr_weight_flip_transpose(const void* w_krsc, void* w_out, int32_t Cout, int32_t Cin, int32_t ksize, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -206,3 +206,37 @@ def test_modweight_matches_oracle(Cout, Cin, k, demod, tr, dtype, tol, built_lib
     oa.backward(up.to(dtype)); ob.backward(up.to(dtype).float())
     _cmp(wa.grad, wb.grad, tol)
     _cmp(sa.grad, sb.grad, 5 * tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,Cin,Cout,k,act,noise", [(16, 16, 64, 64, 3, True, True), (8, 16, 128, 128, 3, False, False),
+                                                    (32, 64, 512, 256, 3, True, False), (64, 64, 64, 128, 1, False, False),
+                                                    (128, 128, 128, 64, 3, True, True), (24, 48, 1024, 512, 3, True, False)])
+def test_tcgen05_conv_matches_fp32_reference(H, W, Cin, Cout, k, act, noise, built_lib):
+    """Implicit-GEMM conv on tcgen05 (bf16 operands, fp32 accumulate) vs an fp32 convolution of the SAME bf16-rounded
+    operands: only the final bf16 rounding of the output differs (<= 2^-8 relative)."""
+    from animatablegaussians_b200 import styleunet_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(1, Cin, H, W, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    nz = torch.randn(1, 1, H, W, device="cuda", generator=g) if noise else None
+    nw = torch.tensor([0.5], device="cuda") if noise else None
+    assert ops._tc_ok(x, Cout, k, 1)
+    xa, wa, ba = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ya = ops._ConvAct.apply(xa, wa, ba, nz, nw, act)
+    xb, wb, bb = x.float().requires_grad_(True), w.float().requires_grad_(True), b.clone().requires_grad_(True)
+    yb = torch.nn.functional.conv2d(xb, wb, None, padding=k // 2)
+    if noise:
+        yb = yb + nw * nz
+    yb = yb + bb.view(1, -1, 1, 1)
+    if act:
+        yb = torch.nn.functional.leaky_relu(yb, 0.2) * 2 ** 0.5
+    _cmp(ya, yb, 8e-3)
+    up = torch.randn(yb.shape, device="cuda", generator=g).to(torch.bfloat16)
+    ya.backward(up)
+    # reference backward starts from the product's own bf16 output sign pattern (lrelu kink) -> use float grads of yb
+    yb.backward(up.float())
+    _cmp(xa.grad, xb.grad, 2e-2)
+    _cmp(wa.grad, wb.grad, 2e-2)
+    _cmp(ba.grad, bb.grad, 2e-2)
