@@ -137,7 +137,7 @@ def test_upfirdn2d_matches_oracle(C, H, W, kind, dtype, tol, built_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])  # oracle = cuDNN fp32 conv (may pick Winograd)
 @pytest.mark.parametrize("C", [3, 8, 12, 64])
 def test_haar_and_wavelet_upsample_match_oracle(C, dtype, tol, built_lib):
     from animatablegaussians_b200 import styleunet_ops as ops
@@ -240,3 +240,23 @@ def test_tcgen05_conv_matches_fp32_reference(H, W, Cin, Cout, k, act, noise, bui
     _cmp(xa.grad, xb.grad, 2e-2)
     _cmp(wa.grad, wb.grad, 2e-2)
     _cmp(ba.grad, bb.grad, 2e-2)
+
+
+@pytest.mark.gpu
+def test_bf16_network_tracks_fp32(built_lib):
+    """bf16 compute (tcgen05 convolutions + bf16 glue kernels) stays within bf16 noise of the fp32 path end to end."""
+    from animatablegaussians_b200 import styleunet_ops as ops
+    cfg, use_view, _ = G.CASES["small"]
+    outs, grads = [], []
+    for dt in (torch.float32, torch.bfloat16):
+        ops.set_compute_dtype(dt)
+        net = _build(cfg).cuda()
+        cond, style, vf1, vf2, up = (t.cuda() if t is not None else None for t in G.inputs(cfg, use_view))
+        cond.requires_grad_(True)
+        out, _ = net([style], cond, randomize_noise=False)
+        (out * up).sum().backward()
+        outs.append(out.detach().double()); grads.append(net.convs1[1].conv.weight.grad.detach().double())
+    ops.set_compute_dtype(torch.float32)
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(outs[1], outs[0]) < 3e-2, rel(outs[1], outs[0])
+    assert rel(grads[1], grads[0]) < 8e-2, rel(grads[1], grads[0])
