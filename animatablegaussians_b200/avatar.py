@@ -151,10 +151,14 @@ class AvatarNet(nn.Module):
 
     # ------------------------------------------------------------------ map -> per-Gaussian gather
     def _gather(self, maps):
-        """(1, 2C, S, S) front|back maps -> (N, C) in cano_smpl_mask order; == cat on W, permute, [mask]."""
+        """(1, 2C, S, S) front|back maps -> (N, C) in cano_smpl_mask order; == cat on W, permute, [mask].
+        A batch (V, 2C, S, S) gives (V, N, C)."""
         C = maps.shape[1] // 2
-        m = maps[0].reshape(2, C, -1)
-        return m[self._half, :, self._pix]
+        if maps.shape[0] == 1:
+            m = maps[0].reshape(2, C, -1)
+            return m[self._half, :, self._pix]
+        m = maps.reshape(maps.shape[0], 2, C, -1)
+        return m[:, self._half, :, self._pix].permute(1, 0, 2).contiguous()   # advanced dims come first: (N,V,C)
 
     def _as_map(self, maps):
         front, back = torch.split(maps, [maps.shape[1] // 2] * 2, 1)
@@ -217,6 +221,25 @@ class AvatarNet(nn.Module):
             front_viewdirs, back_viewdirs = self._viewdir_maps(items, *live, cam_pos=cam_pos)
         w = self.opt.get('weight_viewdirs', 1.)
         return w * self.viewdir_net(front_viewdirs), w * self.viewdir_net(back_viewdirs)
+
+    def get_viewdir_feat_batched(self, live, cam_pos):
+        """get_viewdir_feat (avatar.py:126-147) for V camera centres at once -> two (V,128,S/8,S/8) features."""
+        live_pts, live_nmls = live
+        with torch.no_grad():
+            viewdirs = F.normalize(cam_pos[:, None, :] - live_pts[None], dim=-1, eps=1e-3)           # (V,N,3)
+            if self.training:
+                viewdirs = viewdirs + torch.randn(viewdirs.shape, dtype=viewdirs.dtype, device=viewdirs.device) * 0.1
+            viewdirs = F.normalize(viewdirs, dim=-1, eps=1e-3)
+            viewdirs = (live_nmls[None] * viewdirs).sum(-1)                                            # (V,N)
+            Vn = cam_pos.shape[0]
+            Hm, Wm = self.cano_nml_map.shape[:2]
+            vmap = torch.zeros(Vn, Hm * Wm, dtype=viewdirs.dtype, device=viewdirs.device)
+            vmap[:, self._flat] = viewdirs
+            vmap = F.interpolate(vmap.view(Vn, 1, Hm, Wm), None, 0.5, 'nearest')
+            half = vmap.shape[-1] // 2
+            front, back = torch.split(vmap, [half, half], -1)
+        w = self.opt.get('weight_viewdirs', 1.)
+        return w * self.viewdir_net(front), w * self.viewdir_net(back)
 
     def get_pose_map(self, items):
         live_pts = lbs.skin_points(self.lbs, items['cano2live_jnt_mats_woRoot'], self.init_points)
@@ -287,11 +310,10 @@ class AvatarNet(nn.Module):
             with torch.no_grad():
                 live = lbs.skin_points(self.lbs, items['cano2live_jnt_mats'], self.init_points, self.cano_nmls)
             prefix = self.color_net.forward_prefix([self._color_style()], pose_map[None])
-            cols = []
-            for v in range(V):
-                fv, bv = self.get_viewdir_feat(None, live, cam_pos=views["cam_pos"][v])
-                cols.append(self._gather(self.color_net.forward_view_tail(prefix, fv, bv)))
-            colors = torch.stack(cols, 0)
+            fv, bv = self.get_viewdir_feat_batched(live, views["cam_pos"])
+            colors = self._gather(self.color_net.forward_view_tail(prefix, fv, bv))
+            if V == 1:
+                colors = colors[None]
         else:
             colors, _ = self.get_colors(pose_map)
         pos, rot = lbs.transform_cano2live(self.lbs, items['cano2live_jnt_mats'], cano_pts, rotations)

@@ -46,6 +46,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra TCW_%=;\n\t"
         "TCD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -90,7 +94,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 
 struct ConvParams {
-    int H, W, Cin, Cout, taps, ksize;  // taps = ksize*ksize
+    int N, H, W, Cin, Cout, taps, ksize;  // taps = ksize*ksize; N images share the weights
     const float* bias;     // (Cout) or null
     const float* noise;    // (H*W) or null
     const float* noise_w;  // (1) or null
@@ -110,7 +114,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_w = p.W / TILE_W;
-    const int tile_m = blockIdx.x;
+    const int tiles_img = tiles_w * (p.H / TILE_H);
+    const int img = blockIdx.x / tiles_img;
+    const int tile_m = blockIdx.x - img * tiles_img;
     const int h0 = (tile_m / tiles_w) * TILE_H, w0 = (tile_m % tiles_w) * TILE_W;
     const int n0 = blockIdx.y * BN;
     const int kchunks = p.Cin / BK;
@@ -145,7 +151,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 unsigned char* a_dst = smem + s * STAGE_BYTES;
                 unsigned char* b_dst = a_dst + A_BYTES;
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_3d(a_dst, &map_x, &full_bar[s], ck * BK, w0 + dx, h0 + dy);   // OOB -> zeros = padding
+                tma_load_4d(a_dst, &map_x, &full_bar[s], ck * BK, w0 + dx, h0 + dy, img);   // OOB -> zeros = padding
                 tma_load_3d(b_dst, &map_w, &full_bar[s], ck * BK, tap, n0);
             }
         }
@@ -175,9 +181,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;             // pixel within the tile
         const int h = h0 + row / TILE_W, w = w0 + row % TILE_W;
-        const size_t pix = (size_t)h * p.W + w;
+        const size_t pix = (size_t)h * p.W + w;   // noise is per pixel, shared by the N images
         const float add = (p.noise && p.noise_w) ? p.noise_w[0] * p.noise[pix] : 0.f;
-        __nv_bfloat16* out = p.y + pix * p.Cout + n0;
+        __nv_bfloat16* out = p.y + ((size_t)img * p.H * p.W + pix) * p.Cout + n0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -242,6 +248,18 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+static bool make_map_4d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t b0, uint32_t b1,
+                        uint32_t b2) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {d0, d1, d2, d3};
+    cuuint64_t strides[3] = {d0 * 2, d0 * d1 * 2, d0 * d1 * d2 * 2};
+    cuuint32_t box[4] = {b0, b1, b2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static bool make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
@@ -256,7 +274,7 @@ static bool make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t 
 template <int BN>
 static int launch(const void* x, const void* w, const ConvParams& p, cudaStream_t s) {
     CUtensorMap mx, mw;
-    if (!make_map_3d(&mx, x, (uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, BK, TILE_W, TILE_H)) return AGR_ERR_CUDA;
+    if (!make_map_4d(&mx, x, (uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N, BK, TILE_W, TILE_H)) return AGR_ERR_CUDA;
     if (!make_map_3d(&mw, w, (uint64_t)p.Cin, (uint64_t)p.taps, (uint64_t)p.Cout, BK, 1, BN)) return AGR_ERR_CUDA;
     constexpr int smem = STAGES * (A_BYTES + BN * BK * 2) + 1024;
     static bool attr = false;
@@ -264,7 +282,7 @@ static int launch(const void* x, const void* w, const ConvParams& p, cudaStream_
         if (cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
         attr = true;
     }
-    dim3 grid((p.H / TILE_H) * (p.W / TILE_W), p.Cout / BN);
+    dim3 grid(p.N * (p.H / TILE_H) * (p.W / TILE_W), p.Cout / BN);
     conv_tc_kernel<BN><<<grid, NUM_THREADS, smem, s>>>(mx, mw, p);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
@@ -283,12 +301,13 @@ int agr_conv2d_tc_supported(int32_t H, int32_t W, int32_t Cin, int32_t Cout, int
     return 1;
 }
 
-int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize,
-                          const float* bias, const float* noise, const float* noise_w, int32_t activate, void* cuda_stream) {
+int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                          int32_t ksize, const float* bias, const float* noise, const float* noise_w, int32_t activate,
+                          void* cuda_stream) {
     using namespace agr::tc;
-    if (!x || !w_krsc || !y || !agr_conv2d_tc_supported(H, W, Cin, Cout, ksize)) return AGR_ERR_INVALID_ARGUMENT;
+    if (!x || !w_krsc || !y || N < 1 || !agr_conv2d_tc_supported(H, W, Cin, Cout, ksize)) return AGR_ERR_INVALID_ARGUMENT;
     ConvParams p;
-    p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
+    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
     p.bias = bias; p.noise = noise; p.noise_w = noise_w; p.activate = activate; p.y = static_cast<__nv_bfloat16*>(y);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     if (Cout % 128 == 0) return launch<128>(x, w_krsc, p, s);

@@ -164,7 +164,7 @@ constexpr float kSqrt2 = 1.4142135623730951f;
 template <typename T, bool VECTOR>
 __global__ void __launch_bounds__(256) bias_act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t pixels, int C,
                                                           const float* __restrict__ bias, const float* __restrict__ noise,
-                                                          const float* __restrict__ noise_w, int activate) {
+                                                          const float* __restrict__ noise_w, int64_t nper, int activate) {
     constexpr int VN = VECTOR ? VecOf<T>::N : 1;
     const int cv = C / VN;
     const int64_t total = pixels * cv;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) bias_act_fwd_kernel(const T* __restrict__
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % cv) * VN;
         const int64_t p = idx / cv;
-        const float add = noise ? nw * noise[p] : 0.f;
+        const float add = noise ? nw * noise[p % nper] : 0.f;
         float f[VN];
         if (VECTOR) unpack(*reinterpret_cast<const typename VecOf<T>::V*>(x + p * C + c), f); else f[0] = to_f(x[p * C + c]);
 #pragma unroll
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) bias_act_fwd_kernel(const T* __restrict__
 // in shared memory and added with one atomic per channel per block.
 template <typename T, bool VECTOR>
 __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx,
-                                                          int64_t pixels, int C, const float* __restrict__ noise,
+                                                          int64_t pixels, int C, const float* __restrict__ noise, int64_t nper,
                                                           float* __restrict__ d_bias, float* __restrict__ d_noise_w,
                                                           int activate, int pixels_per_block) {
     constexpr int VN = VECTOR ? VecOf<T>::N : 1;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const T* __restrict__
                 bsum[i] += g[i];
                 psum += g[i];
             }
-            if (noise) nsum += psum * noise[p];
+            if (noise) nsum += psum * noise[p % nper];
             if (VECTOR) { typename VecOf<T>::V v; pack(g, v); *reinterpret_cast<typename VecOf<T>::V*>(dx + p * C + my_c) = v; }
             else dx[p * C + my_c] = from_f<T>(g[0]);
         }
@@ -376,8 +376,9 @@ int agr_haar(int32_t dtype, int32_t mode, const void* x, void* y, int32_t N, int
 }
 
 int agr_bias_act_forward(int32_t dtype, const void* x, void* y, int64_t pixels, int32_t C, const float* bias, const float* noise,
-                         const float* noise_w, int32_t activate, void* cuda_stream) {
-    if (!x || !y || pixels < 0 || C < 1) return AGR_ERR_INVALID_ARGUMENT;
+                         const float* noise_w, int64_t noise_period, int32_t activate, void* cuda_stream) {
+    if (!x || !y || pixels < 0 || C < 1 || (noise && noise_period < 1)) return AGR_ERR_INVALID_ARGUMENT;
+    if (!noise) noise_period = 1;
     if (pixels == 0) return AGR_OK;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     const int VN = dtype == AGR_BF16 ? 8 : 4;
@@ -386,18 +387,19 @@ int agr_bias_act_forward(int32_t dtype, const void* x, void* y, int64_t pixels, 
     int g = grid_for(total); if (g > 148 * 32) g = 148 * 32;
     if (dtype == AGR_BF16) {
         using T = __nv_bfloat16;
-        if (vec) bias_act_fwd_kernel<T, true><<<g, 256, 0, s>>>((const T*)x, (T*)y, pixels, C, bias, noise, noise_w, activate);
-        else bias_act_fwd_kernel<T, false><<<g, 256, 0, s>>>((const T*)x, (T*)y, pixels, C, bias, noise, noise_w, activate);
+        if (vec) bias_act_fwd_kernel<T, true><<<g, 256, 0, s>>>((const T*)x, (T*)y, pixels, C, bias, noise, noise_w, noise_period, activate);
+        else bias_act_fwd_kernel<T, false><<<g, 256, 0, s>>>((const T*)x, (T*)y, pixels, C, bias, noise, noise_w, noise_period, activate);
     } else {
-        if (vec) bias_act_fwd_kernel<float, true><<<g, 256, 0, s>>>((const float*)x, (float*)y, pixels, C, bias, noise, noise_w, activate);
-        else bias_act_fwd_kernel<float, false><<<g, 256, 0, s>>>((const float*)x, (float*)y, pixels, C, bias, noise, noise_w, activate);
+        if (vec) bias_act_fwd_kernel<float, true><<<g, 256, 0, s>>>((const float*)x, (float*)y, pixels, C, bias, noise, noise_w, noise_period, activate);
+        else bias_act_fwd_kernel<float, false><<<g, 256, 0, s>>>((const float*)x, (float*)y, pixels, C, bias, noise, noise_w, noise_period, activate);
     }
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 
 int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx, int64_t pixels, int32_t C, const float* noise,
-                          float* d_bias, float* d_noise_w, int32_t activate, void* cuda_stream) {
-    if (!dy || !dx || (activate && !y) || pixels < 0 || C < 1) return AGR_ERR_INVALID_ARGUMENT;
+                          int64_t noise_period, float* d_bias, float* d_noise_w, int32_t activate, void* cuda_stream) {
+    if (!dy || !dx || (activate && !y) || pixels < 0 || C < 1 || (noise && noise_period < 1)) return AGR_ERR_INVALID_ARGUMENT;
+    if (!noise) noise_period = 1;
     if (pixels == 0) return AGR_OK;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     const int VN = dtype == AGR_BF16 ? 8 : 4;
@@ -411,11 +413,11 @@ int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx
     const size_t smem = (size_t)(C + 1) * sizeof(float);
     if (dtype == AGR_BF16) {
         using T = __nv_bfloat16;
-        if (vec) bias_act_bwd_kernel<T, true><<<(unsigned)blocks, 256, smem, s>>>((const T*)dy, (const T*)y, (T*)dx, pixels, C, noise, d_bias, d_noise_w, activate, ppb);
-        else bias_act_bwd_kernel<T, false><<<(unsigned)blocks, 256, smem, s>>>((const T*)dy, (const T*)y, (T*)dx, pixels, C, noise, d_bias, d_noise_w, activate, ppb);
+        if (vec) bias_act_bwd_kernel<T, true><<<(unsigned)blocks, 256, smem, s>>>((const T*)dy, (const T*)y, (T*)dx, pixels, C, noise, noise_period, d_bias, d_noise_w, activate, ppb);
+        else bias_act_bwd_kernel<T, false><<<(unsigned)blocks, 256, smem, s>>>((const T*)dy, (const T*)y, (T*)dx, pixels, C, noise, noise_period, d_bias, d_noise_w, activate, ppb);
     } else {
-        if (vec) bias_act_bwd_kernel<float, true><<<(unsigned)blocks, 256, smem, s>>>((const float*)dy, (const float*)y, (float*)dx, pixels, C, noise, d_bias, d_noise_w, activate, ppb);
-        else bias_act_bwd_kernel<float, false><<<(unsigned)blocks, 256, smem, s>>>((const float*)dy, (const float*)y, (float*)dx, pixels, C, noise, d_bias, d_noise_w, activate, ppb);
+        if (vec) bias_act_bwd_kernel<float, true><<<(unsigned)blocks, 256, smem, s>>>((const float*)dy, (const float*)y, (float*)dx, pixels, C, noise, noise_period, d_bias, d_noise_w, activate, ppb);
+        else bias_act_bwd_kernel<float, false><<<(unsigned)blocks, 256, smem, s>>>((const float*)dy, (const float*)y, (float*)dx, pixels, C, noise, noise_period, d_bias, d_noise_w, activate, ppb);
     }
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }

@@ -200,7 +200,7 @@ class StyledConv(nn.Module):
         s = c.modulation(style)
         if noise is None:  # randomize_noise=True path of the reference (dual_styleunet.py:309-313)
             h = x.shape[2] * (2 if c.upsample else 1)
-            noise = x.new_empty(x.shape[0], 1, h, h).normal_()
+            noise = x.new_empty(1, 1, h, h).normal_()
         return ops.modulated_conv2d(x, c.weight, s, c.scale, demodulate=c.demodulate, upsample=c.upsample,
                                     downsample=c.downsample, blur=getattr(c, "blur", None), padding=c.padding,
                                     noise=noise, noise_weight=self.noise.weight, act_bias=self.activate.bias,
@@ -341,7 +341,10 @@ class DualStyleUNet(nn.Module):
             if i == 0:
                 out = self.comb_convs[-1](cond_list[-1])
             elif i < 2 * len(self.comb_convs):
-                out = self.comb_convs[-1 - lvl](torch.cat([out, cond_list[-1 - lvl]], dim=1))
+                cond = cond_list[-1 - lvl]
+                if cond.shape[0] != out.shape[0]:
+                    cond = cond.expand(out.shape[0], -1, -1, -1)
+                out = self.comb_convs[-1 - lvl](torch.cat([out, cond], dim=1))
             out = convs[i](out, latent[:, i], noise=noise[i])
             out = convs[i + 1](out, latent[:, i + 1], noise=noise[i + 1])
             skip = to_rgbs[lvl](out, latent[:, i + 2], skip)
@@ -379,13 +382,21 @@ class DualStyleUNet(nn.Module):
         return dict(latent=latent, noise=noise, cond_list=cond_list, s1=s1, s2=s2)
 
     def forward_view_tail(self, prefix, view_feature1, view_feature2):
-        """Per-view remainder: add the (bilinearly resized) view feature, run the last decoder level(s)."""
+        """View-dependent remainder for a BATCH of V views (view features (V,128,h,w)): add the (bilinearly resized)
+        view feature to the shared prefix state, run the last decoder level(s) once with batch V — every layer's
+        modulated weight is prepared once and shared by the V views."""
         outs = []
+        V = view_feature1.shape[0] if view_feature1 is not None else 1
         for convs, rgbs, st, vf in ((self.convs1, self.to_rgbs1, prefix["s1"], view_feature1),
                                     (self.convs2, self.to_rgbs2, prefix["s2"], view_feature2)):
             out, skip = st
             if vf is not None and self.view_level < 2 * len(rgbs):  # smaller nets never reach the view level
                 out = out + ops.bilinear_resize(vf, out.shape[-2:])
+            if V > 1:
+                if out.shape[0] == 1:
+                    out = out.expand(V, -1, -1, -1)
+                if skip is not None and skip.shape[0] == 1:
+                    skip = skip.expand(V, -1, -1, -1)
             outs.append(self._decode(convs, rgbs, prefix["cond_list"], prefix["latent"], prefix["noise"], None,
                                      start=self.view_level + 2, state=(out, skip)))
         return ops.from_compute(torch.cat(outs, 1))

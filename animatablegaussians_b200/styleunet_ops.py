@@ -30,12 +30,12 @@ _p = C.c_void_p
 _lib.register_symbols({
     "agr_upfirdn2d": (C.c_int, [C.c_int32, _p, _p] + [C.c_int32] * 6 + [C.POINTER(C.c_float)] + [C.c_int32] * 6 + [_p]),
     "agr_haar": (C.c_int, [C.c_int32, C.c_int32, _p, _p] + [C.c_int32] * 4 + [_p]),
-    "agr_bias_act_forward": (C.c_int, [C.c_int32, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int32, _p]),
-    "agr_bias_act_backward": (C.c_int, [C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int32, _p]),
+    "agr_bias_act_forward": (C.c_int, [C.c_int32, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, _p]),
+    "agr_bias_act_backward": (C.c_int, [C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, _p, C.c_int64, _p, _p, C.c_int32, _p]),
     "agr_modweight_forward": (C.c_int, [C.c_int32, _p, _p, C.c_float] + [C.c_int32] * 5 + [_p, _p, _p]),
     "agr_modweight_backward": (C.c_int, [C.c_int32, _p, _p, C.c_float] + [C.c_int32] * 5 + [_p, _p, _p, _p, _p]),
     "agr_conv2d_tc_supported": (C.c_int, [C.c_int32] * 5),
-    "agr_conv2d_tc_forward": (C.c_int, [_p, _p, _p] + [C.c_int32] * 5 + [_p, _p, _p, C.c_int32, _p]),
+    "agr_conv2d_tc_forward": (C.c_int, [_p, _p, _p] + [C.c_int32] * 6 + [_p, _p, _p, C.c_int32, _p]),
     "agr_weight_flip_transpose": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
 })
 
@@ -199,10 +199,11 @@ class _BiasAct(torch.autograd.Function):
         b = bias.detach().float().contiguous() if bias is not None else None
         nz = noise.detach().float().contiguous() if noise is not None else None
         nw = noise_weight.detach().float().contiguous() if noise_weight is not None else None
-        if nz is not None and nz.numel() != pixels:
-            raise RuntimeError("noise must have one value per pixel")
+        nper = nz.numel() if nz is not None else 1
+        if nz is not None and pixels % nper != 0:
+            raise RuntimeError("noise must have one value per pixel (one image shared by the batch)")
         with torch.cuda.device(x.device), stats.stage("styleunet_act", launches=1):
-            _check(lib.agr_bias_act_forward(_code(x), _ptr(x), _ptr(y), pixels, Cc, _ptr(b), _ptr(nz), _ptr(nw), int(activate),
+            _check(lib.agr_bias_act_forward(_code(x), _ptr(x), _ptr(y), pixels, Cc, _ptr(b), _ptr(nz), _ptr(nw), nper, int(activate),
                                             _stream(x)), "agr_bias_act_forward")
         ctx.save_for_backward(y if activate else None, nz)
         ctx.meta = (activate, is4, bias is not None, noise_weight is not None and noise is not None, Cc, pixels,
@@ -220,7 +221,8 @@ class _BiasAct(torch.autograd.Function):
         dn = torch.zeros(1, dtype=torch.float32, device=g.device) if has_n else None
         with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
             _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dx), pixels, Cc, _ptr(nz) if has_n else None,
-                                             _ptr(db), _ptr(dn), int(activate), _stream(g)), "agr_bias_act_backward")
+                                             nz.numel() if has_n else 1, _ptr(db), _ptr(dn), int(activate), _stream(g)),
+                   "agr_bias_act_backward")
         return dx, (db.view(bshape) if has_b else None), None, (dn.view(nshape) if has_n else None), None
 
 
@@ -281,7 +283,7 @@ def _ones(n, dev):
 
 # ------------------------------------------------------------------------------------------ dense contractions
 def _tc_ok(x, Cout, k, stride):
-    if x.dtype != torch.bfloat16 or stride != 1 or x.shape[0] != 1:
+    if x.dtype != torch.bfloat16 or stride != 1:
         return False
     return bool(_lib.load().agr_conv2d_tc_supported(x.shape[2], x.shape[3], x.shape[1], Cout, k))
 
@@ -291,7 +293,7 @@ def _tc_conv(x, w, Cout, k, bias, noise, noise_w, activate):
     lib = _lib.load()
     y = _new_like(x, Cout, x.shape[2], x.shape[3])
     with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=1):
-        _check(lib.agr_conv2d_tc_forward(_ptr(x), _ptr(w), _ptr(y), x.shape[2], x.shape[3], x.shape[1], Cout, k, _ptr(bias),
+        _check(lib.agr_conv2d_tc_forward(_ptr(x), _ptr(w), _ptr(y), x.shape[0], x.shape[2], x.shape[3], x.shape[1], Cout, k, _ptr(bias),
                                          _ptr(noise), _ptr(noise_w), int(activate), _stream(x)), "agr_conv2d_tc_forward")
     return y
 
@@ -321,14 +323,15 @@ class _ConvAct(torch.autograd.Function):
         activate, k, has_b, has_n, bshape, nshape = ctx.meta
         Cout, Cin = w.shape[0], w.shape[1]
         g = _nhwc(g)
-        pixels = g.shape[2] * g.shape[3]
+        pixels = g.shape[0] * g.shape[2] * g.shape[3]
         if activate or has_b or has_n:
             dz = torch.empty_like(g)
             db = torch.zeros(Cout, dtype=torch.float32, device=g.device) if has_b else None
             dn = torch.zeros(1, dtype=torch.float32, device=g.device) if has_n else None
             with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
                 _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dz), pixels, Cout, _ptr(nz) if has_n else None,
-                                                 _ptr(db), _ptr(dn), int(activate), _stream(g)), "agr_bias_act_backward")
+                                                 nz.numel() if has_n else 1, _ptr(db), _ptr(dn), int(activate), _stream(g)),
+                       "agr_bias_act_backward")
         else:
             dz, db, dn = g, None, None
         dx = dw = None
@@ -359,8 +362,8 @@ def equal_conv2d(x, weight, scale, stride, padding, act_bias=None, activate=True
 
 def modulated_conv2d(x, weight, s, scale, demodulate=True, upsample=False, downsample=False, blur=None, padding=1,
                      noise=None, noise_weight=None, act_bias=None, activate=True):
-    if x.shape[0] != 1:
-        raise RuntimeError("the avatar path runs the StyleUNets at batch 1 (one pose); got batch %d" % x.shape[0])
+    if s.shape[0] != 1:
+        raise RuntimeError("one style per call: the batch (views of one pose) shares the modulated weight")
     w = _ModWeight.apply(weight, s, scale, demodulate, upsample, x.dtype)
     if upsample:
         out = blur(F.conv_transpose2d(x, w, padding=0, stride=2))

@@ -40,13 +40,16 @@ int agr_haar(int32_t dtype, int32_t mode, const void* x, void* y, int32_t N, int
              void* cuda_stream);
 
 /* y = act(x + noise_w[0] * noise[n? no: h][w] + bias[c]),  act = lrelu(.,0.2)*sqrt(2) if activate else identity.
- * noise: (H,W) fp32 or NULL; noise_w: 1 fp32 on device or NULL; bias: (C) fp32 or NULL. */
+ * noise: (H,W) fp32 or NULL, indexed with pixel % noise_period (= H*W: one noise image shared by the batch);
+ * noise_w: 1 fp32 on device or NULL; bias: (C) fp32 or NULL. */
 int agr_bias_act_forward(int32_t dtype, const void* x, void* y, int64_t pixels, int32_t C, const float* bias,
-                         const float* noise, const float* noise_w, int32_t activate, void* cuda_stream);
+                         const float* noise, const float* noise_w, int64_t noise_period, int32_t activate,
+                         void* cuda_stream);
 /* dx = dy * (activate ? (y > 0 ? sqrt2 : 0.2*sqrt2) : 1); d_bias[c] += sum dx; d_noise_w[0] += sum dx*noise.
  * d_bias / d_noise_w (fp32) are ACCUMULATED into (caller zeroes); either may be NULL. y is the forward OUTPUT. */
 int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx, int64_t pixels, int32_t C,
-                          const float* noise, float* d_bias, float* d_noise_w, int32_t activate, void* cuda_stream);
+                          const float* noise, int64_t noise_period, float* d_bias, float* d_noise_w, int32_t activate,
+                          void* cuda_stream);
 
 /* Modulated-convolution weight: w_out[co][ky][kx][ci] (KRSC, dtype) = scale*w[co][ci][ky][kx]*s[ci]*demod[co],
  * demod[co] = rsqrt(sum_{ci,k} (scale*w*s)^2 + 1e-8) if demodulate else 1.  w fp32 (Cout,Cin,k,k), s fp32 (Cin).
@@ -62,15 +65,16 @@ int agr_modweight_backward(int32_t dtype, const float* w, const float* s, float 
                            const float* demod, float* d_w, float* d_s, void* cuda_stream);
 
 /* ---- dense contraction on the tensor cores (tcgen05.mma + TMA, bf16 in / fp32 accumulate / bf16 out) ----
- * Stride-1 "same" convolution, batch 1, NHWC:  y = act(conv(x, w) + noise_w*noise + bias).
- *   x (H,W,Cin) bf16, w_krsc (Cout, k, k, Cin) bf16 (what agr_modweight_forward writes), y (H,W,Cout) bf16,
- *   bias (Cout) fp32 / noise (H,W) fp32 / noise_w (1) fp32 may be NULL; activate: lrelu(0.2)*sqrt(2).
+ * Stride-1 "same" convolution, NHWC, N images sharing one weight (the view batch of the colour-net tail):
+ *   y = act(conv(x, w) + noise_w*noise + bias).
+ *   x (N,H,W,Cin) bf16, w_krsc (Cout, k, k, Cin) bf16 (what agr_modweight_forward writes), y (N,H,W,Cout) bf16,
+ *   bias (Cout) fp32 / noise (H,W) fp32 (shared by the N images) / noise_w (1) fp32 may be NULL; activate: lrelu(0.2)*sqrt(2).
  * Shapes must satisfy agr_conv2d_tc_supported (H % 8 == 0, W % 16 == 0, Cin % 64 == 0, Cout % 64 == 0, k in {1,3}).
  * The data gradient of the same convolution is this call on dy with agr_weight_flip_transpose(w). */
 int agr_conv2d_tc_supported(int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);
-int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                          int32_t ksize, const float* bias, const float* noise, const float* noise_w, int32_t activate,
-                          void* cuda_stream);
+int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin,
+                          int32_t Cout, int32_t ksize, const float* bias, const float* noise, const float* noise_w,
+                          int32_t activate, void* cuda_stream);
 /* w_out[ci][k*k-1-t][co] = w_krsc[co][t][ci]  (bf16) */
 int agr_weight_flip_transpose(const void* w_krsc, void* w_out, int32_t Cout, int32_t Cin, int32_t ksize, void* cuda_stream);
 

@@ -122,17 +122,18 @@ def test_upfirdn2d_matches_oracle(C, H, W, kind, dtype, tol, built_lib):
     from animatablegaussians_b200 import styleunet_ops as ops
     from oracle import styleunet_oracle as so
     k = so.make_kernel([1, 3, 3, 1]).cuda()
+    kd = k.double()
     cfg = {"blur1": dict(kernel=k * 4, up=1, down=1, pad=(1, 1)), "blur2": dict(kernel=k, up=1, down=1, pad=(2, 2)),
            "up": dict(kernel=k * 4, up=2, down=1, pad=(2, 1)), "down": dict(kernel=k, up=1, down=2, pad=(1, 1))}[kind]
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(1, C, H, W, device="cuda", generator=g)
     xa = x.to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    xb = x.to(dtype).float().requires_grad_(True)
+    xb = x.to(dtype).double().requires_grad_(True)
     ya = ops.upfirdn2d(xa, **cfg)
-    yb = so.upfirdn2d(xb, **cfg)
+    yb = so.upfirdn2d(xb, **dict(cfg, kernel=cfg['kernel'].double()))
     _cmp(ya, yb, tol)
     up = torch.randn(yb.shape, device="cuda", generator=g)
-    ya.backward(up.to(dtype)); yb.backward(up.to(dtype).float())
+    ya.backward(up.to(dtype)); yb.backward(up.to(dtype).double())
     _cmp(xa.grad, xb.grad, tol)
 
 
@@ -145,17 +146,17 @@ def test_haar_and_wavelet_upsample_match_oracle(C, dtype, tol, built_lib):
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.randn(1, C, 24, 16, device="cuda", generator=g).to(dtype)
     xa = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    xb = x.float().requires_grad_(True)
+    xb = x.double().requires_grad_(True)
     ya, yb = ops.haar_dwt(xa), so.haar_dwt(xb)
     _cmp(ya, yb, tol)
     _cmp(ops.haar_iwt(ya), so.haar_iwt(yb), tol)
     _cmp(ops.haar_iwt(ya), x, 2 * tol)  # orthonormal round trip
     k = (so.make_kernel([1, 3, 3, 1]) * 4).cuda()
     if C % 4 == 0:
-        za, zb = ops.wavelet_upsample(xa, k), so.wavelet_upsample(xb, k)
+        za, zb = ops.wavelet_upsample(xa, k), so.wavelet_upsample(xb, k.double())
         _cmp(za, zb, 2 * tol)
         up = torch.randn(zb.shape, device="cuda", generator=g)
-        za.backward(up.to(dtype)); zb.backward(up.to(dtype).float())
+        za.backward(up.to(dtype)); zb.backward(up.to(dtype).double())
         _cmp(xa.grad, xb.grad, 3 * tol)
 
 
@@ -167,18 +168,18 @@ def test_bias_act_matches_oracle(C, H, activate, noise, dtype, tol, built_lib):
     from oracle import styleunet_oracle as so
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.randn(1, C, H, H, device="cuda", generator=g).to(dtype)
-    ba, bb = (torch.randn(C, device="cuda", generator=g).requires_grad_(True) for _ in range(2))
-    bb.data.copy_(ba.data)
+    ba = torch.randn(C, device="cuda", generator=g).requires_grad_(True)
+    bb = ba.detach().double().requires_grad_(True)
     nz = torch.randn(1, 1, H, H, device="cuda", generator=g) if noise else None
     wa = torch.tensor([0.37], device="cuda", requires_grad=True) if noise else None
-    wb = torch.tensor([0.37], device="cuda", requires_grad=True) if noise else None
+    wb = torch.tensor([0.37], device="cuda", dtype=torch.float64, requires_grad=True) if noise else None
     xa = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    xb = x.float().requires_grad_(True)
+    xb = x.double().requires_grad_(True)
     ya = ops.bias_act(xa, ba, nz, wa, activate)
-    yb = so.bias_act(xb, bb, nz, wb, activate)
+    yb = so.bias_act(xb, bb, nz.double() if noise else None, wb, activate)
     _cmp(ya, yb, tol)
     up = torch.randn(yb.shape, device="cuda", generator=g)
-    ya.backward(up.to(dtype)); yb.backward(up.to(dtype).float())
+    ya.backward(up.to(dtype)); yb.backward(up.to(dtype).double())
     _cmp(xa.grad, xb.grad, tol)
     _cmp(ba.grad, bb.grad, 5 * tol)
     if noise:
@@ -196,14 +197,14 @@ def test_modweight_matches_oracle(Cout, Cin, k, demod, tr, dtype, tol, built_lib
     s = 1 + 0.3 * torch.randn(1, Cin, device="cuda", generator=g)
     scale = 1 / (Cin * k * k) ** 0.5
     wa, sa = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
-    wb, sb = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    wb, sb = w.double().requires_grad_(True), s.double().requires_grad_(True)
     oa = ops._ModWeight.apply(wa, sa, scale, demod, tr, dtype)
     ob = so.prepare_modulated_weight(wb, sb, scale, demod)[0]
     if tr:
         ob = ob.transpose(0, 1)
     _cmp(oa, ob, tol)
     up = torch.randn(ob.shape, device="cuda", generator=g)
-    oa.backward(up.to(dtype)); ob.backward(up.to(dtype).float())
+    oa.backward(up.to(dtype)); ob.backward(up.to(dtype).double())
     _cmp(wa.grad, wb.grad, tol)
     _cmp(sa.grad, sb.grad, 5 * tol)
 
