@@ -47,10 +47,14 @@ struct FirParams {
     int kh, kw, up, down, pad_x0, pad_y0;
 };
 
-template <typename T, bool VECTOR>
+// UP / DOWN / K are compile-time (0 = generic run-time values): the zero-inserted taps of an upsampling filter are
+// skipped at compile time (4 of 16 loads survive for up=2), all index divisions strength-reduce, and the tap loops unroll.
+template <typename T, bool VECTOR, int UP_, int DOWN_, int K_>
 __global__ void __launch_bounds__(256) upfirdn_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C,
                                                      int outH, int outW, FirParams fp) {
     constexpr int VN = VECTOR ? VecOf<T>::N : 1;
+    const int up = UP_ ? UP_ : fp.up, down = DOWN_ ? DOWN_ : fp.down;
+    const int kh = K_ ? K_ : fp.kh, kw = K_ ? K_ : fp.kw;
     const int cv = C / VN;
     const int64_t total = (int64_t)N * outH * outW * cv;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,19 +67,27 @@ __global__ void __launch_bounds__(256) upfirdn_kernel(const T* __restrict__ x, T
     float acc[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) acc[i] = 0.f;
-    const int by = oy * fp.down - fp.pad_y0, bx = ox * fp.down - fp.pad_x0;
-    for (int ky = 0; ky < fp.kh; ++ky) {
+    const int by = oy * down - fp.pad_y0, bx = ox * down - fp.pad_x0;
+    // first tap whose upsampled coordinate is a multiple of `up`:  (b + k) % up == 0
+    const int ky0 = (up == 1) ? 0 : ((up - (by % up + up) % up) % up);
+    const int kx0 = (up == 1) ? 0 : ((up - (bx % up + up) % up) % up);
+    const T* xn = x + (int64_t)n * H * W * C + (int64_t)c * VN;
+#pragma unroll
+    for (int kyi = 0; kyi < (K_ ? (K_ + (UP_ ? UP_ : 1) - 1) / (UP_ ? UP_ : 1) : 64); ++kyi) {
+        const int ky = ky0 + kyi * up;
+        if (ky >= kh) break;
         const int uy = by + ky;
-        if (uy < 0 || (uy % fp.up) != 0) continue;
-        const int iy = uy / fp.up;
-        if (iy >= H) continue;
-        for (int kx = 0; kx < fp.kw; ++kx) {
+        const int iy = (up == 1) ? uy : uy / up;   // uy % up == 0 by construction (uy may be negative: C division is fine, multiple of up)
+        if (uy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kxi = 0; kxi < (K_ ? (K_ + (UP_ ? UP_ : 1) - 1) / (UP_ ? UP_ : 1) : 64); ++kxi) {
+            const int kx = kx0 + kxi * up;
+            if (kx >= kw) break;
             const int ux = bx + kx;
-            if (ux < 0 || (ux % fp.up) != 0) continue;
-            const int ix = ux / fp.up;
-            if (ix >= W) continue;
-            const float t = fp.taps[ky * fp.kw + kx];
-            const T* src = x + (((int64_t)n * H + iy) * W + ix) * C + (int64_t)c * VN;
+            const int ix = (up == 1) ? ux : ux / up;
+            if (ux < 0 || ix >= W) continue;
+            const float t = fp.taps[ky * kw + kx];
+            const T* src = xn + ((int64_t)iy * W + ix) * C;
             if (VECTOR) {
                 float f[VN];
                 unpack(*reinterpret_cast<const typename VecOf<T>::V*>(src), f);
@@ -339,14 +351,23 @@ int agr_upfirdn2d(int32_t dtype, const void* x, void* y, int32_t N, int32_t H, i
     for (int i = 0; i < kh * kw; ++i) fp.taps[i] = taps[i];
     fp.kh = kh; fp.kw = kw; fp.up = up; fp.down = down; fp.pad_x0 = pad_x0; fp.pad_y0 = pad_y0;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+#define AGR_FIR_LAUNCH(T, VEC, VN, U, D, K)                                                                             \
+    upfirdn_kernel<T, VEC, U, D, K><<<grid_for((int64_t)N * out_h * out_w * (C / VN)), 256, 0, s>>>(                    \
+        (const T*)x, (T*)y, N, H, W, C, out_h, out_w, fp)
+#define AGR_FIR_SHAPE(T, VEC, VN)                                                                                       \
+    do {                                                                                                                \
+        if (kh == 4 && kw == 4 && up == 1 && down == 1) AGR_FIR_LAUNCH(T, VEC, VN, 1, 1, 4);                            \
+        else if (kh == 4 && kw == 4 && up == 2 && down == 1) AGR_FIR_LAUNCH(T, VEC, VN, 2, 1, 4);                       \
+        else if (kh == 4 && kw == 4 && up == 1 && down == 2) AGR_FIR_LAUNCH(T, VEC, VN, 1, 2, 4);                       \
+        else AGR_FIR_LAUNCH(T, VEC, VN, 0, 0, 0);                                                                       \
+    } while (0)
     if (dtype == AGR_BF16) {
-        using T = __nv_bfloat16;
-        if (C % 8 == 0) upfirdn_kernel<T, true><<<grid_for((int64_t)N * out_h * out_w * (C / 8)), 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C, out_h, out_w, fp);
-        else upfirdn_kernel<T, false><<<grid_for((int64_t)N * out_h * out_w * C), 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C, out_h, out_w, fp);
+        if (C % 8 == 0) AGR_FIR_SHAPE(__nv_bfloat16, true, 8); else AGR_FIR_SHAPE(__nv_bfloat16, false, 1);
     } else {
-        if (C % 4 == 0) upfirdn_kernel<float, true><<<grid_for((int64_t)N * out_h * out_w * (C / 4)), 256, 0, s>>>((const float*)x, (float*)y, N, H, W, C, out_h, out_w, fp);
-        else upfirdn_kernel<float, false><<<grid_for((int64_t)N * out_h * out_w * C), 256, 0, s>>>((const float*)x, (float*)y, N, H, W, C, out_h, out_w, fp);
+        if (C % 4 == 0) AGR_FIR_SHAPE(float, true, 4); else AGR_FIR_SHAPE(float, false, 1);
     }
+#undef AGR_FIR_SHAPE
+#undef AGR_FIR_LAUNCH
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 

@@ -94,21 +94,28 @@ def _new_like(x, C_, H, W):
 
 
 # ------------------------------------------------------------------------------------------ FIR resampling
+import weakref  # noqa: E402
+
 _taps_cache = {}
 
 
 def _host_taps(kernel, flip):
-    """(kh,kw) device buffer -> ctypes float array (flipped or not); cached, one D2H per distinct kernel."""
-    key = (kernel.data_ptr(), tuple(kernel.shape), flip, kernel._version)
+    """(kh,kw) device buffer -> ctypes float array (flipped or not).  Cached per tensor OBJECT (weak reference +
+    version counter, so a recycled address or an in-place update can never serve stale taps): one D2H per FIR buffer
+    of the module, none afterwards (required for CUDA-graph capture)."""
+    key = (id(kernel), flip)
     hit = _taps_cache.get(key)
-    if hit is None:
-        k = kernel.detach().float().cpu()
-        if flip:
-            k = torch.flip(k, [0, 1])
-        vals = [float(v) for v in k.reshape(-1)]
-        hit = ((C.c_float * len(vals))(*vals), int(k.shape[0]), int(k.shape[1]))
-        _taps_cache[key] = hit
-    return hit
+    if hit is not None and hit[0]() is kernel and hit[1] == kernel._version:
+        return hit[2]
+    k = kernel.detach().float().cpu()
+    if flip:
+        k = torch.flip(k, [0, 1])
+    vals = [float(v) for v in k.reshape(-1)]
+    out = ((C.c_float * len(vals))(*vals), int(k.shape[0]), int(k.shape[1]))
+    if len(_taps_cache) > 4096:
+        _taps_cache.clear()
+    _taps_cache[key] = (weakref.ref(kernel), kernel._version, out)
+    return out
 
 
 def _fir_launch(x, taps, kh, kw, up, down, px0, py0, out_h, out_w):

@@ -63,7 +63,10 @@ def test_oracle_pinned_by_reference_kernels(name, ref_available):
     want = Hn.run_reference(sc, g)
     got = util.run_oracle(sc, g, alpha_from=want["alpha"])
     assert got["R"] == want["R"]
-    Hn.compare(name, got, want, util.TOL, util.assert_close)
+    # 2e-4: the CPU oracle's fp32 rounding differs from the GPU's, so a pixel whose transmittance lands within an ulp of
+    # the T < 1e-4 termination test (forward.cu:351) can stop one Gaussian earlier/later: a colour change < 1e-4 ABSOLUTE
+    # by construction.  (The product is held to 1e-4 against the reference kernels themselves.)
+    Hn.compare(name, got, want, 2 * util.TOL, util.assert_close)
 
 
 def test_empty_input(built_lib):
