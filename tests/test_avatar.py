@@ -35,8 +35,8 @@ def test_render_views_equals_per_view_render(built_lib):
         for v in range(len(extrs)):
             it = dict(items, extr=torch.from_numpy(extrs[v]).cuda(), intr=torch.from_numpy(Ks[v]).cuda(), img_w=img, img_h=img)
             single = net.render(it, bg_color=(0.2, 0.4, 0.6))
-            util.assert_close("rgb v%d" % v, batched["rgb_maps"][v].cpu().numpy(), single["rgb_map"].cpu().numpy(), 1e-3)
-            util.assert_close("mask v%d" % v, batched["mask_maps"][v].cpu().numpy(), single["mask_map"].cpu().numpy(), 1e-3)
+            util.assert_close_robust("rgb v%d" % v, batched["rgb_maps"][v].cpu().numpy(), single["rgb_map"].cpu().numpy(), 1e-4)
+            util.assert_close_robust("mask v%d" % v, batched["mask_maps"][v].cpu().numpy(), single["mask_map"].cpu().numpy(), 1e-4)
     assert batched["rgb_maps"].shape == (len(extrs), img, img, 3)
     assert float(batched["mask_maps"].max()) > 0.5  # the avatar is actually in view
 

@@ -92,3 +92,16 @@ def run_oracle(sc, grads=None, alpha_from=None):
     if grads is not None:
         out["grads"] = o.backward(*grads, alpha_override=alpha_from)
     return out
+
+
+def assert_close_robust(name, a, b, tol=TOL, outlier_frac=1e-4, outlier_tol=2e-2):
+    """For comparisons that cross the rasterizer's discrete decisions (alpha >= 1/255, T < 1e-4): all but a
+    vanishing fraction of the elements must agree to `tol`, and no element may be off by more than `outlier_tol`
+    (relative to max|b|)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max(), 1e-30)
+    err = np.abs(a - b) / scale
+    frac = float((err > tol).mean())
+    assert frac <= outlier_frac, "%s: %.2e of the elements differ by more than %.1e" % (name, frac, tol)
+    assert err.max() <= outlier_tol, "%s: worst element off by %.2e" % (name, err.max())
