@@ -78,6 +78,9 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_bwd_kernel(BlendBwdParams 
     const float ddely_dy = 0.5 * p.H;
 
     float* acc_view = p.acc + (size_t)v * p.P * AGR_ACC_STRIDE;
+    const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
+    const float bx0 = (float)(tile_x * AGR_TILE_X + (warp & 1) * 8), bx1 = bx0 + 7.f;
+    const float by0 = (float)(tile_y * AGR_TILE_Y + (warp >> 1) * 4), by1 = by0 + 3.f;
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
     uint32_t phase0 = 0, phase1 = 0;
 
@@ -93,7 +96,22 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_bwd_kernel(BlendBwdParams 
         if (buf == 0) { mbar_wait(&s_bar[0], phase0); phase0 ^= 1; }
         else          { mbar_wait(&s_bar[1], phase1); phase1 ^= 1; }
 
-        for (int j = hi - lo - 1; j >= 0; --j) {
+        const int n = hi - lo;
+        for (int c = ((n - 1) / 32) * 32; c >= 0; c -= 32) {
+          // sub-tile culling (see blend_fwd): lane l tests record c+l — inside the warp's reach (k < warp_last) and its
+          // footprint box overlapping the warp's 8x4 pixel block; survivors are replayed back to front.
+          const int jl = c + (int)lane;
+          bool hit = false;
+          if (jl < n && (uint32_t)(lo + jl) < warp_last) {
+              const float4 t0 = s_rec[buf][jl].q0;
+              const float2 ext = unpack_extent(s_rec[buf][jl].q2.w);
+              hit = (t0.x + ext.x >= bx0) && (t0.x - ext.x <= bx1) && (t0.y + ext.y >= by0) && (t0.y - ext.y <= by1);
+          }
+          uint32_t mask = __ballot_sync(0xffffffffu, hit);
+          while (mask) {
+            const int b = 31 - __clz(mask);
+            mask &= ~(1u << b);
+            const int j = c + b;
             const uint32_t k = (uint32_t)(lo + j);  // position in the tile list == reference `contributor`
             const float4 q0 = s_rec[buf][j].q0;
             const float4 q1 = s_rec[buf][j].q1;
@@ -195,6 +213,7 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_bwd_kernel(BlendBwdParams 
             } else if ((lane & 15) == 2) {
                 atomicAdd(dst + 8 + (b4 ? 1 : 0), z);
             }
+          }
         }
     }
 }

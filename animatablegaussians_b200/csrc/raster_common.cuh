@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstddef>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 #define AGR_TILE_X 16
 #define AGR_TILE_Y 16
@@ -140,6 +141,30 @@ __device__ __forceinline__ float3 cov2d_project(const float3& mean, float focal_
     return make_float3(cov.c[0][0] + 0.3f, cov.c[0][1], cov.c[1][1] + 0.3f);
 }
 
+// Conservative footprint of one projected Gaussian.  A pixel at offset d contributes only if
+//   power = -1/2 d^T A d <= 0  and  o * exp(power) >= 1/255   (forward.cu:339-349),  A = [[a,b],[b,c]] the conic,
+// i.e. inside the ellipse 1/2 d^T A d <= tau, tau = ln(255 o).  Its bounding box has half-sizes
+//   hx = sqrt(2 tau (A^-1)_xx) = sqrt(2 tau c / det),  hy = sqrt(2 tau a / det).
+// Inflated by 1e-3 relative + 0.01 px (orders of magnitude above the fp32 rounding of `power`), +inf when the conic
+// is not positive definite, negative ("never") when o < 1/255.  Returned as half2 bits, rounded up.
+__device__ __forceinline__ uint32_t footprint_half_extent(float a, float b, float c, float o) {
+    float hx, hy;
+    const float det = a * c - b * b;
+    if (o < 1.0f / 255.0f) { hx = -1.f; hy = -1.f; }
+    else if (!(det > 0.f) || !(a > 0.f) || !(c > 0.f)) { hx = hy = __int_as_float(0x7f800000); }
+    else {
+        const float tau2 = 2.0f * logf(255.0f * o) + 1e-4f;
+        hx = sqrtf(fmaxf(tau2 * c / det, 0.f)) * 1.001f + 0.01f;
+        hy = sqrtf(fmaxf(tau2 * a / det, 0.f)) * 1.001f + 0.01f;
+    }
+    const __half2 h = __halves2half2(__float2half_ru(hx), __float2half_ru(hy));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_extent(float bits) {
+    const uint32_t u = __float_as_uint(bits);
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+
 // ------------------------------------------------------------------ SH constants ----
 __device__ const float kSH_C0 = 0.28209479177387814f;
 __device__ const float kSH_C1 = 0.4886025119029199f;
@@ -156,7 +181,9 @@ struct __align__(16) GeomRec { float4 a, b; };
 
 // Per-instance record of the depth-sorted, tile-major attribute stream (48 B) that the
 // blend kernels stream through shared memory:
-//   q0 = (px, py, conic_a, conic_b)  q1 = (conic_c, opacity, r, g)  q2 = (b, z_view, id bits, 0)
+//   q0 = (px, py, conic_a, conic_b)  q1 = (conic_c, opacity, r, g)  q2 = (b, z_view, id bits, extent)
+// extent = half2 (hx, hy), rounded UP: half-sizes of the axis-aligned box around the ellipse outside of which the
+// Gaussian cannot reach alpha >= 1/255 (see footprint_half_extent); lets a warp skip Gaussians that miss its pixels.
 struct __align__(16) InstRec { float4 q0, q1, q2; };
 
 // Per-(view, Gaussian) gradient accumulator filled by the blend backward (64 B):

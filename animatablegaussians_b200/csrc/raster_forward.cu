@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(GatherParams p) {
     InstRec out;
     out.q0 = rec.a;
     out.q1 = make_float4(rec.b.x, rec.b.y, col[0], col[1]);
-    out.q2 = make_float4(col[2], rec.b.z, __uint_as_float(g), 0.f);
+    out.q2 = make_float4(col[2], rec.b.z, __uint_as_float(g),
+                         __uint_as_float(footprint_half_extent(rec.a.z, rec.a.w, rec.b.x, rec.b.y)));
     p.stream[i] = out;
 }
 
@@ -231,7 +232,9 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_fwd_kernel(BlendFwdParams 
 
     bool done = !inside;
     float T = 1.0f;
-    uint32_t contributor = 0, last_contributor = 0;
+    uint32_t last_contributor = 0;
+    const float bx0 = (float)(tile_x * AGR_TILE_X + (warp & 1) * 8), bx1 = bx0 + 7.f;
+    const float by0 = (float)(tile_y * AGR_TILE_Y + (warp >> 1) * 4), by1 = by0 + 3.f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, weight = 0.f, D = 0.f;
     int toDo = total;
     uint32_t phase0 = 0, phase1 = 0;
@@ -250,25 +253,41 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_fwd_kernel(BlendFwdParams 
         else          { mbar_wait(&s_bar[1], phase1); phase1 ^= 1; }
 
         const int n = min(BATCH, toDo);
-        for (int j = 0; !done && j < n; ++j) {
-            contributor++;
-            const float4 q0 = s_rec[buf][j].q0;
-            const float4 q1 = s_rec[buf][j].q1;
-            const float2 d = make_float2(q0.x - pixf.x, q0.y - pixf.y);
-            const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
-            if (power > 0.0f) continue;
-            const float alpha = min(0.99f, q1.y * expf(power));
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = T * (1 - alpha);
-            if (test_T < 0.0001f) { done = true; continue; }
-            const float4 q2 = s_rec[buf][j].q2;
-            C0 += q1.z * alpha * T;
-            C1 += q1.w * alpha * T;
-            C2 += q2.x * alpha * T;
-            weight += alpha * T;
-            D += q2.y * alpha * T;
-            T = test_T;
-            last_contributor = contributor;
+        // Sub-tile culling: lane l tests record c+l against this warp's 8x4 pixel block (bounding-box overlap with
+        // the Gaussian's alpha >= 1/255 footprint); the warp then walks only the surviving records, in list order.
+        for (int c = 0; c < n; c += 32) {
+            if (__all_sync(0xffffffffu, done)) break;
+            const int jl = c + (int)lane;
+            bool hit = false;
+            if (jl < n) {
+                const float4 t0 = s_rec[buf][jl].q0;
+                const float2 ext = unpack_extent(s_rec[buf][jl].q2.w);
+                hit = (t0.x + ext.x >= bx0) && (t0.x - ext.x <= bx1) && (t0.y + ext.y >= by0) && (t0.y - ext.y <= by1);
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (done) continue;
+                const int j = c + b;
+                const float4 q0 = s_rec[buf][j].q0;
+                const float4 q1 = s_rec[buf][j].q1;
+                const float2 d = make_float2(q0.x - pixf.x, q0.y - pixf.y);
+                const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
+                if (power > 0.0f) continue;
+                const float alpha = min(0.99f, q1.y * expf(power));
+                if (alpha < 1.0f / 255.0f) continue;
+                const float test_T = T * (1 - alpha);
+                if (test_T < 0.0001f) { done = true; continue; }
+                const float4 q2 = s_rec[buf][j].q2;
+                C0 += q1.z * alpha * T;
+                C1 += q1.w * alpha * T;
+                C2 += q2.x * alpha * T;
+                weight += alpha * T;
+                D += q2.y * alpha * T;
+                T = test_T;
+                last_contributor = (uint32_t)(i * BATCH + j + 1);   // == the reference's running `contributor`
+            }
         }
     }
 

@@ -334,6 +334,25 @@ __global__ void __launch_bounds__(256) modweight_bwd_kernel(const float* __restr
     }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) sum_batch_kernel(const T* __restrict__ x, T* __restrict__ y, int V, int64_t nvec) {
+    constexpr int VN = VecOf<T>::N;
+    using Vt = typename VecOf<T>::V;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float acc[VN];
+#pragma unroll
+        for (int k = 0; k < VN; ++k) acc[k] = 0.f;
+        for (int v = 0; v < V; ++v) {
+            float f[VN];
+            unpack(reinterpret_cast<const Vt*>(x)[(int64_t)v * nvec + i], f);
+#pragma unroll
+            for (int k = 0; k < VN; ++k) acc[k] += f[k];
+        }
+        Vt o; pack(acc, o);
+        reinterpret_cast<Vt*>(y)[i] = o;
+    }
+}
+
 inline int grid_for(int64_t total, int block = 256) { return (int)((total + block - 1) / block); }
 
 }  // namespace agr
@@ -440,6 +459,19 @@ int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx
         if (vec) bias_act_bwd_kernel<float, true><<<(unsigned)blocks, 256, smem, s>>>((const float*)dy, (const float*)y, (float*)dx, pixels, C, noise, noise_period, d_bias, d_noise_w, activate, ppb);
         else bias_act_bwd_kernel<float, false><<<(unsigned)blocks, 256, smem, s>>>((const float*)dy, (const float*)y, (float*)dx, pixels, C, noise, noise_period, d_bias, d_noise_w, activate, ppb);
     }
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_sum_batch(int32_t dtype, const void* x, void* y, int32_t V, int64_t n, void* cuda_stream) {
+    if (!x || !y || V < 1 || n < 0) return AGR_ERR_INVALID_ARGUMENT;
+    const int VN = dtype == AGR_BF16 ? 8 : 4;
+    if (n % VN) return AGR_ERR_INVALID_ARGUMENT;
+    if (n == 0) return AGR_OK;
+    const int64_t nvec = n / VN;
+    int g = grid_for(nvec); if (g > 148 * 16) g = 148 * 16;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    if (dtype == AGR_BF16) sum_batch_kernel<__nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, V, nvec);
+    else sum_batch_kernel<float><<<g, 256, 0, s>>>((const float*)x, (float*)y, V, nvec);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 

@@ -343,7 +343,7 @@ class DualStyleUNet(nn.Module):
             elif i < 2 * len(self.comb_convs):
                 cond = cond_list[-1 - lvl]
                 if cond.shape[0] != out.shape[0]:
-                    cond = cond.expand(out.shape[0], -1, -1, -1)
+                    cond = ops.expand_batch(cond, out.shape[0])
                 out = self.comb_convs[-1 - lvl](torch.cat([out, cond], dim=1))
             out = convs[i](out, latent[:, i], noise=noise[i])
             out = convs[i + 1](out, latent[:, i + 1], noise=noise[i + 1])
@@ -390,13 +390,12 @@ class DualStyleUNet(nn.Module):
         for convs, rgbs, st, vf in ((self.convs1, self.to_rgbs1, prefix["s1"], view_feature1),
                                     (self.convs2, self.to_rgbs2, prefix["s2"], view_feature2)):
             out, skip = st
+            if V > 1:
+                out = ops.expand_batch(out, V)
+                if skip is not None:
+                    skip = ops.expand_batch(skip, V)
             if vf is not None and self.view_level < 2 * len(rgbs):  # smaller nets never reach the view level
                 out = out + ops.bilinear_resize(vf, out.shape[-2:])
-            if V > 1:
-                if out.shape[0] == 1:
-                    out = out.expand(V, -1, -1, -1)
-                if skip is not None and skip.shape[0] == 1:
-                    skip = skip.expand(V, -1, -1, -1)
             outs.append(self._decode(convs, rgbs, prefix["cond_list"], prefix["latent"], prefix["noise"], None,
                                      start=self.view_level + 2, state=(out, skip)))
         return ops.from_compute(torch.cat(outs, 1))

@@ -37,6 +37,7 @@ _lib.register_symbols({
     "agr_conv2d_tc_supported": (C.c_int, [C.c_int32] * 5),
     "agr_conv2d_tc_forward": (C.c_int, [_p, _p, _p] + [C.c_int32] * 6 + [_p, _p, _p, C.c_int32, _p]),
     "agr_weight_flip_transpose": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
+    "agr_sum_batch": (C.c_int, [C.c_int32, _p, _p, C.c_int32, C.c_int64, _p]),
 })
 
 _COMPUTE_DTYPE = torch.float32
@@ -191,6 +192,34 @@ def wavelet_upsample(skip, up_kernel):
     y = haar_iwt(skip)
     y = upfirdn2d(y, up_kernel, up=2, pad=((p + 1) // 2 + 1, p // 2))
     return haar_dwt(y)
+
+
+class _ExpandBatch(torch.autograd.Function):
+    """(1,C,H,W) -> (V,C,H,W) broadcast view of the shared prefix state; the adjoint sums the V gradients with one
+    streaming kernel."""
+
+    @staticmethod
+    def forward(ctx, x, V):
+        ctx.V = V
+        return x.expand(V, -1, -1, -1)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        g = _nhwc(g)
+        y = _new_like(g[:1], g.shape[1], g.shape[2], g.shape[3])
+        n = y.numel()
+        with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
+            _check(lib.agr_sum_batch(_code(g), _ptr(g), _ptr(y), ctx.V, n, _stream(g)), "agr_sum_batch")
+        return y, None
+
+
+def expand_batch(x, V):
+    if V == 1 or x.shape[0] == V:
+        return x
+    if x.numel() % 8:
+        return x.expand(V, -1, -1, -1)
+    return _ExpandBatch.apply(_nhwc(x), V)
 
 
 # ------------------------------------------------------------------------------------------ bias + noise + act

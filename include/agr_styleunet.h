@@ -75,6 +75,10 @@ int agr_conv2d_tc_supported(int32_t H, int32_t W, int32_t Cin, int32_t Cout, int
 int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin,
                           int32_t Cout, int32_t ksize, const float* bias, const float* noise, const float* noise_w,
                           int32_t activate, void* cuda_stream);
+/* y[i] = sum_v x[v][i], i < n  (fp32 accumulate): the adjoint of broadcasting the shared colour-net prefix state to the
+ * V views of a batch (ATen's strided reduction reaches ~0.3 TB/s on this shape; this streams at HBM rate). */
+int agr_sum_batch(int32_t dtype, const void* x, void* y, int32_t V, int64_t n, void* cuda_stream);
+
 /* w_out[ci][k*k-1-t][co] = w_krsc[co][t][ci]  (bf16) */
 int agr_weight_flip_transpose(const void* w_krsc, void* w_out, int32_t Cout, int32_t Cin, int32_t ksize, void* cuda_stream);
 
