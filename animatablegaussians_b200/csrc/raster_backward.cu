@@ -21,10 +21,11 @@
 namespace agr {
 
 // ------------------------------------------------------------------ blend (backward)
-template <int BATCH>
-__global__ void __launch_bounds__(AGR_TILE_PIX) blend_bwd_kernel(BlendBwdParams p) {
-    __shared__ __align__(128) InstRec s_rec[2][BATCH];
-    __shared__ __align__(8) uint64_t s_bar[2];
+template <int BATCH, int STAGES>
+__global__ void __launch_bounds__(AGR_TILE_PIX + 32) blend_bwd_kernel(BlendBwdParams p) {
+    __shared__ __align__(128) InstRec s_rec[STAGES][BATCH];
+    __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES];
+    constexpr uint32_t NCONS = AGR_TILE_PIX / 32;
 
     const uint32_t tile_lin = blockIdx.x;
     const uint32_t L = p.tile_last[tile_lin];  // entries [0, L) of this tile's list can matter
@@ -45,14 +46,21 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_bwd_kernel(BlendBwdParams 
     const int rounds = (int)((L + BATCH - 1) / BATCH);
 
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NCONS); }
         fence_mbar_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const int hi = (int)L, lo = max(0, hi - BATCH);
-        bulk_load(&s_rec[0][0], src + lo, (uint32_t)(hi - lo) * sizeof(InstRec), &s_bar[0]);
+    if (warp == NCONS) {
+        // ================= producer warp: streams the list back to front through the ring =================
+        if (lane == 0) {
+            for (int i = 0; i < rounds; ++i) {
+                const int s = i % STAGES;
+                if (i >= STAGES) mbar_wait(&s_empty[s], ((i / STAGES) & 1) ^ 1);
+                const int hi = (int)L - i * BATCH, lo = max(0, hi - BATCH);
+                bulk_load(&s_rec[s][0], src + lo, (uint32_t)(hi - lo) * sizeof(InstRec), &s_full[s]);
+            }
+        }
+        return;  // consumers wait on every full barrier, so no copy outlives the CTA
     }
 
     const float T_final = inside ? (1 - p.out_alpha[v * HW + pix_id]) : 0;
@@ -82,19 +90,12 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_bwd_kernel(BlendBwdParams 
     const float bx0 = (float)(tile_x * AGR_TILE_X + (warp & 1) * 8), bx1 = bx0 + 7.f;
     const float by0 = (float)(tile_y * AGR_TILE_Y + (warp >> 1) * 4), by1 = by0 + 3.f;
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-    uint32_t phase0 = 0, phase1 = 0;
 
     for (int i = 0; i < rounds; ++i) {
-        const int buf = i & 1;
+        const int buf = i % STAGES;
         const int hi = (int)L - i * BATCH;
         const int lo = max(0, hi - BATCH);
-        __syncthreads();  // everyone is done with buffer buf^1 (round i-1)
-        if (threadIdx.x == 0 && i + 1 < rounds) {
-            const int hi1 = lo, lo1 = max(0, hi1 - BATCH);
-            bulk_load(&s_rec[buf ^ 1][0], src + lo1, (uint32_t)(hi1 - lo1) * sizeof(InstRec), &s_bar[buf ^ 1]);
-        }
-        if (buf == 0) { mbar_wait(&s_bar[0], phase0); phase0 ^= 1; }
-        else          { mbar_wait(&s_bar[1], phase1); phase1 ^= 1; }
+        mbar_wait(&s_full[buf], (i / STAGES) & 1);
 
         const int n = hi - lo;
         for (int c = ((n - 1) / 32) * 32; c >= 0; c -= 32) {
@@ -215,6 +216,8 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_bwd_kernel(BlendBwdParams 
             }
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[buf]);
     }
 }
 
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdParams
 }
 
 void launch_blend_bwd(const BlendBwdParams& p, cudaStream_t s) {
-    blend_bwd_kernel<AGR_BATCH><<<p.num_tiles_total, AGR_TILE_PIX, 0, s>>>(p);
+    blend_bwd_kernel<AGR_BATCH, AGR_STAGES><<<p.num_tiles_total, AGR_TILE_PIX + 32, 0, s>>>(p);
 }
 void launch_preprocess_bwd(const PreprocessBwdParams& p, const ViewScalars& vs, cudaStream_t s) {
     preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, vs);

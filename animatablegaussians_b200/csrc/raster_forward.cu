@@ -192,76 +192,86 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(GatherParams p) {
 }
 
 // --------------------------------------------------------------------------- blend (forward)
-// One CTA per 16x16 tile; 8 warps, each owning an 8x4 pixel block.  The sorted attribute
-// stream of the tile is staged through shared memory in batches of AGR_BATCH records with
-// cp.async.bulk (TMA bulk copy, mbarrier completion), double-buffered so the copy of batch
-// k+1 overlaps the blending of batch k.  Per-pixel arithmetic and its order are exactly
-// forward.cu:329-368.
-template <int BATCH>
-__global__ void __launch_bounds__(AGR_TILE_PIX) blend_fwd_kernel(BlendFwdParams p) {
-    __shared__ __align__(128) InstRec s_rec[2][BATCH];
-    __shared__ __align__(8) uint64_t s_bar[2];
+// One CTA per 16x16 tile: 8 CONSUMER warps, each owning an 8x4 pixel block, plus 1 PRODUCER warp.  The producer streams
+// the tile's depth-sorted attribute records through a ring of AGR_STAGES shared-memory buffers with cp.async.bulk
+// (TMA bulk copy) and full/empty mbarriers; consumers never meet at a block-wide barrier, so a warp whose pixels saturate
+// early or whose block is missed by most Gaussians (sub-tile culling below) runs ahead instead of waiting for its siblings.
+// Per-pixel arithmetic and its order are exactly forward.cu:329-368.
+template <int BATCH, int STAGES>
+__global__ void __launch_bounds__(AGR_TILE_PIX + 32) blend_fwd_kernel(BlendFwdParams p) {
+    __shared__ __align__(128) InstRec s_rec[STAGES][BATCH];
+    __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES];
     __shared__ uint32_t s_warp_last[AGR_TILE_PIX / 32];
+    __shared__ int s_warps_done;
 
     const uint32_t tile_lin = blockIdx.x;  // view*tiles + tile
     const uint32_t v = tile_lin / p.tiles_per_view;
     const uint32_t t = tile_lin - v * p.tiles_per_view;
     const uint32_t tile_y = t / p.grid_x, tile_x = t - tile_y * p.grid_x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t px = tile_x * AGR_TILE_X + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = tile_y * AGR_TILE_Y + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
-    const float2 pixf = make_float2((float)px, (float)py);
+    constexpr uint32_t NCONS = AGR_TILE_PIX / 32;
 
     const uint2 range = p.ranges[tile_lin];
     const int total = (int)(range.y - range.x);
     const int rounds = (total + BATCH - 1) / BATCH;
+    const InstRec* src = p.stream + range.x;
 
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NCONS); }
+        s_warps_done = 0;
         fence_mbar_init();
     }
     __syncthreads();
 
-    const InstRec* src = p.stream + range.x;
-    if (threadIdx.x == 0 && rounds > 0) {
-        const int n0 = min(BATCH, total);
-        bulk_load(&s_rec[0][0], src, (uint32_t)n0 * sizeof(InstRec), &s_bar[0]);
+    if (warp == NCONS) {
+        // ================= producer warp (one elected lane) =================
+        if (lane == 0) {
+            int issued = 0;
+            for (int i = 0; i < rounds; ++i) {
+                const int s = i % STAGES;
+                if (i >= STAGES) mbar_wait(&s_empty[s], ((i / STAGES) & 1) ^ 1);
+                if (*(volatile int*)&s_warps_done == (int)NCONS) break;   // every pixel of the tile is finished
+                const int n = min(BATCH, total - i * BATCH);
+                bulk_load(&s_rec[s][0], src + (size_t)i * BATCH, (uint32_t)n * sizeof(InstRec), &s_full[s]);
+                issued = i + 1;
+            }
+            // no copy may be in flight when the CTA retires: wait for the (at most STAGES) youngest ones
+            for (int i = max(0, issued - STAGES); i < issued; ++i) mbar_wait(&s_full[i % STAGES], (i / STAGES) & 1);
+        }
+        return;
     }
 
+    // ================= consumer warps =================
+    const uint32_t px = tile_x * AGR_TILE_X + (warp & 1) * 8 + (lane & 7);
+    const uint32_t py = tile_y * AGR_TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
+    const float2 pixf = make_float2((float)px, (float)py);
     bool done = !inside;
     float T = 1.0f;
     uint32_t last_contributor = 0;
     const float bx0 = (float)(tile_x * AGR_TILE_X + (warp & 1) * 8), bx1 = bx0 + 7.f;
     const float by0 = (float)(tile_y * AGR_TILE_Y + (warp >> 1) * 4), by1 = by0 + 3.f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, weight = 0.f, D = 0.f;
-    int toDo = total;
-    uint32_t phase0 = 0, phase1 = 0;
+    bool warp_done = false;
 
-    int i = 0;
-    for (; i < rounds; ++i, toDo -= BATCH) {
-        // all warps finished with buffer (i+1)&1 (used by round i-1) once they pass this barrier
-        const int num_done = __syncthreads_count(done);
-        if (num_done == AGR_TILE_PIX) break;
-        const int buf = i & 1;
-        if (threadIdx.x == 0 && i + 1 < rounds) {
-            const int n1 = min(BATCH, total - (i + 1) * BATCH);
-            bulk_load(&s_rec[buf ^ 1][0], src + (size_t)(i + 1) * BATCH, (uint32_t)n1 * sizeof(InstRec), &s_bar[buf ^ 1]);
+    for (int i = 0; i < rounds; ++i) {
+        if (!warp_done && __all_sync(0xffffffffu, done)) {
+            warp_done = true;
+            if (lane == 0) atomicAdd(&s_warps_done, 1);
         }
-        if (buf == 0) { mbar_wait(&s_bar[0], phase0); phase0 ^= 1; }
-        else          { mbar_wait(&s_bar[1], phase1); phase1 ^= 1; }
-
-        const int n = min(BATCH, toDo);
+        if (*(volatile int*)&s_warps_done == (int)NCONS) break;   // uniform per warp: one shared word
+        const int s = i % STAGES;
+        mbar_wait(&s_full[s], (i / STAGES) & 1);
+        const int n = min(BATCH, total - i * BATCH);
         // Sub-tile culling: lane l tests record c+l against this warp's 8x4 pixel block (bounding-box overlap with
         // the Gaussian's alpha >= 1/255 footprint); the warp then walks only the surviving records, in list order.
-        for (int c = 0; c < n; c += 32) {
+        for (int c = 0; c < n && !warp_done; c += 32) {
             if (__all_sync(0xffffffffu, done)) break;
             const int jl = c + (int)lane;
             bool hit = false;
             if (jl < n) {
-                const float4 t0 = s_rec[buf][jl].q0;
-                const float2 ext = unpack_extent(s_rec[buf][jl].q2.w);
+                const float4 t0 = s_rec[s][jl].q0;
+                const float2 ext = unpack_extent(s_rec[s][jl].q2.w);
                 hit = (t0.x + ext.x >= bx0) && (t0.x - ext.x <= bx1) && (t0.y + ext.y >= by0) && (t0.y - ext.y <= by1);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
@@ -270,8 +280,8 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_fwd_kernel(BlendFwdParams 
                 mask &= mask - 1;
                 if (done) continue;
                 const int j = c + b;
-                const float4 q0 = s_rec[buf][j].q0;
-                const float4 q1 = s_rec[buf][j].q1;
+                const float4 q0 = s_rec[s][j].q0;
+                const float4 q1 = s_rec[s][j].q1;
                 const float2 d = make_float2(q0.x - pixf.x, q0.y - pixf.y);
                 const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
                 if (power > 0.0f) continue;
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_fwd_kernel(BlendFwdParams 
                 if (alpha < 1.0f / 255.0f) continue;
                 const float test_T = T * (1 - alpha);
                 if (test_T < 0.0001f) { done = true; continue; }
-                const float4 q2 = s_rec[buf][j].q2;
+                const float4 q2 = s_rec[s][j].q2;
                 C0 += q1.z * alpha * T;
                 C1 += q1.w * alpha * T;
                 C2 += q2.x * alpha * T;
@@ -289,12 +299,14 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_fwd_kernel(BlendFwdParams 
                 last_contributor = (uint32_t)(i * BATCH + j + 1);   // == the reference's running `contributor`
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);
     }
-
-    if (i < rounds) {
-        // early exit with the copy of batch i still in flight: it must land before this CTA's
-        // shared memory can be handed to another CTA
-        if ((i & 1) == 0) mbar_wait(&s_bar[0], phase0); else mbar_wait(&s_bar[1], phase1);
+    // Leaving early (whole tile saturated) must not strand the producer on an `empty` barrier: one extra arrival per
+    // warp and stage completes whatever phase it is waiting for; it then sees s_warps_done == NCONS and stops.
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_arrive(&s_empty[s]);
     }
 
     if (inside) {
@@ -313,7 +325,7 @@ __global__ void __launch_bounds__(AGR_TILE_PIX) blend_fwd_kernel(BlendFwdParams 
     uint32_t m = inside ? last_contributor : 0u;
     m = __reduce_max_sync(0xffffffffu, m);
     if (lane == 0) s_warp_last[warp] = m;
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"r"(AGR_TILE_PIX) : "memory");   // the 8 consumer warps only
     if (threadIdx.x == 0) {
         uint32_t mm = 0;
 #pragma unroll
@@ -358,7 +370,7 @@ void launch_ranges_gather(const GatherParams& p, cudaStream_t s) {
     ranges_gather_kernel<<<(p.R + 255) / 256, 256, 0, s>>>(p);
 }
 void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t s) {
-    blend_fwd_kernel<AGR_BATCH><<<p.num_tiles_total, AGR_TILE_PIX, 0, s>>>(p);
+    blend_fwd_kernel<AGR_BATCH, AGR_STAGES><<<p.num_tiles_total, AGR_TILE_PIX + 32, 0, s>>>(p);
 }
 void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s) {
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);

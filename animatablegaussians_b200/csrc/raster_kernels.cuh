@@ -7,6 +7,9 @@
 #ifndef AGR_BATCH
 #define AGR_BATCH 128  // instance records staged per shared-memory batch (128 * 48 B = 6 KB)
 #endif
+#ifndef AGR_STAGES
+#define AGR_STAGES 4   // ring depth of the producer/consumer pipeline of the blend kernels (24 KB)
+#endif
 
 namespace agr {
 
