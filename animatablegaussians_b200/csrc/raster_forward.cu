@@ -229,8 +229,15 @@ __global__ void __launch_bounds__(AGR_TILE_PIX + 32) blend_fwd_kernel(BlendFwdPa
             int issued = 0;
             for (int i = 0; i < rounds; ++i) {
                 const int s = i % STAGES;
-                if (i >= STAGES) mbar_wait(&s_empty[s], ((i / STAGES) & 1) ^ 1);
-                if (*(volatile int*)&s_warps_done == (int)NCONS) break;   // every pixel of the tile is finished
+                bool all_done = false;
+                if (i >= STAGES) {
+                    // wait for the stage to be released — or for the whole tile to finish, in which case the consumers
+                    // have stopped arriving and nothing more must be fetched
+                    while (!mbar_try_wait(&s_empty[s], ((i / STAGES) & 1) ^ 1)) {
+                        if (*(volatile int*)&s_warps_done == (int)NCONS) { all_done = true; break; }
+                    }
+                }
+                if (all_done || *(volatile int*)&s_warps_done == (int)NCONS) break;   // every pixel of the tile is finished
                 const int n = min(BATCH, total - i * BATCH);
                 bulk_load(&s_rec[s][0], src + (size_t)i * BATCH, (uint32_t)n * sizeof(InstRec), &s_full[s]);
                 issued = i + 1;
@@ -302,13 +309,6 @@ __global__ void __launch_bounds__(AGR_TILE_PIX + 32) blend_fwd_kernel(BlendFwdPa
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[s]);
     }
-    // Leaving early (whole tile saturated) must not strand the producer on an `empty` barrier: one extra arrival per
-    // warp and stage completes whatever phase it is waiting for; it then sees s_warps_done == NCONS and stops.
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_arrive(&s_empty[s]);
-    }
-
     if (inside) {
         const size_t HW = (size_t)p.H * p.W;
         const size_t pix_id = (size_t)p.W * py + px;

@@ -40,6 +40,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "AGR_DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// single probe (the instruction itself blocks for a bounded, implementation-defined time, then reports false)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 // bytes must be a multiple of 16; src/dst 16-byte aligned.
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
