@@ -266,9 +266,18 @@ __global__ void __launch_bounds__(AGR_TILE_PIX + 32) blend_fwd_kernel(BlendFwdPa
             warp_done = true;
             if (lane == 0) atomicAdd(&s_warps_done, 1);
         }
-        if (*(volatile int*)&s_warps_done == (int)NCONS) break;   // uniform per warp: one shared word
         const int s = i % STAGES;
-        mbar_wait(&s_full[s], (i / STAGES) & 1);
+        // Wait for batch i — or for the tile to be finished (all 8 warps saturated), after which the producer stops
+        // fetching and batch i may never arrive.  Lane 0 polls, the verdict is broadcast so the warp leaves together.
+        int stop = 0;
+        if (lane == 0) {
+            while (!mbar_try_wait(&s_full[s], (i / STAGES) & 1)) {
+                if (*(volatile int*)&s_warps_done == (int)NCONS) { stop = 1; break; }
+            }
+        }
+        stop = __shfl_sync(0xffffffffu, stop, 0);
+        if (stop) break;
+        mbar_wait(&s_full[s], (i / STAGES) & 1);   // already complete: per-thread acquire of the TMA-written data
         const int n = min(BATCH, total - i * BATCH);
         // Sub-tile culling: lane l tests record c+l against this warp's 8x4 pixel block (bounding-box overlap with
         // the Gaussian's alpha >= 1/255 footprint); the warp then walks only the surviving records, in list order.
