@@ -22,7 +22,7 @@ namespace agr {
 
 // ------------------------------------------------------------------ blend (backward)
 template <int BATCH, int STAGES>
-__global__ void __launch_bounds__(AGR_TILE_PIX + 32) blend_bwd_kernel(BlendBwdParams p) {
+__global__ void __launch_bounds__(AGR_TILE_PIX + 32, 4) blend_bwd_kernel(BlendBwdParams p) {
     __shared__ __align__(128) InstRec s_rec[STAGES][BATCH];
     __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES];
     constexpr uint32_t NCONS = AGR_TILE_PIX / 32;
