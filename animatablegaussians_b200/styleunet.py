@@ -342,9 +342,12 @@ class DualStyleUNet(nn.Module):
                 out = self.comb_convs[-1](cond_list[-1])
             elif i < 2 * len(self.comb_convs):
                 cond = cond_list[-1 - lvl]
-                if cond.shape[0] != out.shape[0]:
-                    cond = ops.expand_batch(cond, out.shape[0])
-                out = self.comb_convs[-1 - lvl](torch.cat([out, cond], dim=1))
+                comb = self.comb_convs[-1 - lvl]
+                if cond.shape[0] != out.shape[0]:   # view batch: the skip feature is shared -> split contraction
+                    conv = comb[0]
+                    out = ops.equal_conv2d_split(out, cond, conv.weight, conv.scale, act_bias=comb[1].bias, activate=True)
+                else:
+                    out = comb(torch.cat([out, cond], dim=1))
             out = convs[i](out, latent[:, i], noise=noise[i])
             out = convs[i + 1](out, latent[:, i + 1], noise=noise[i + 1])
             skip = to_rgbs[lvl](out, latent[:, i + 2], skip)

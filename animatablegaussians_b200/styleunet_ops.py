@@ -38,6 +38,7 @@ _lib.register_symbols({
     "agr_conv2d_tc_forward": (C.c_int, [_p, _p, _p] + [C.c_int32] * 6 + [_p, _p, _p, C.c_int32, _p]),
     "agr_weight_flip_transpose": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
     "agr_sum_batch": (C.c_int, [C.c_int32, _p, _p, C.c_int32, C.c_int64, _p]),
+    "agr_conv2d_tc_forward_split": (C.c_int, [_p, _p, _p] + [C.c_int32] * 8 + [_p, _p, C.c_int32, _p]),
 })
 
 _COMPUTE_DTYPE = torch.float32
@@ -384,6 +385,76 @@ class _ConvAct(torch.autograd.Function):
             dw = torch.ops.aten.convolution_backward(dz, x, w, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
                                                      [False, True, False])[1]
         return dx, dw, (db.view(bshape) if has_b else None), None, (dn.view(nshape) if has_n else None), None
+
+
+def _tc_conv_split(x, w, Cout, k, cin_total, cin_offset, residual, bias, activate):
+    lib = _lib.load()
+    y = _new_like(x, Cout, x.shape[2], x.shape[3])
+    with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=1):
+        _check(lib.agr_conv2d_tc_forward_split(_ptr(x), _ptr(w), _ptr(y), x.shape[0], x.shape[2], x.shape[3], x.shape[1], Cout, k,
+                                               cin_total, cin_offset, _ptr(residual), _ptr(bias), int(activate), _stream(x)),
+               "agr_conv2d_tc_forward_split")
+    return y
+
+
+class _SplitConvAct(torch.autograd.Function):
+    """act(conv(cat([a (V,Ca,H,W), b (1,Cb,H,W) broadcast]), w) + bias) without the concatenation: the view-independent
+    half conv(b, w[:, Ca:]) runs once and enters the per-view half as a residual in the tcgen05 epilogue."""
+
+    @staticmethod
+    def forward(ctx, a, b, w, bias, activate):
+        a, b = _nhwc(a), _nhwc(b)
+        w = w.contiguous(memory_format=_CL)
+        Cout, k, Ca, Cb = w.shape[0], w.shape[-1], a.shape[1], b.shape[1]
+        bb = bias.detach().float().contiguous() if bias is not None else None
+        zb = _tc_conv_split(b, w, Cout, k, Ca + Cb, Ca, None, None, False)
+        y = _tc_conv_split(a, w, Cout, k, Ca + Cb, 0, zb, bb, activate)
+        ctx.save_for_backward(a, b, w, y if activate else None)
+        ctx.meta = (activate, k, bias is not None, None if bias is None else bias.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        a, b, w, y = ctx.saved_tensors
+        activate, k, has_b, bshape = ctx.meta
+        Cout, Ca, Cb, V = w.shape[0], a.shape[1], b.shape[1], a.shape[0]
+        g = _nhwc(g)
+        pixels = g.shape[0] * g.shape[2] * g.shape[3]
+        dz = torch.empty_like(g)
+        db = torch.zeros(Cout, dtype=torch.float32, device=g.device) if has_b else None
+        with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
+            _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dz), pixels, Cout, None, 1, _ptr(db), None,
+                                             int(activate), _stream(g)), "agr_bias_act_backward")
+        dzs = _new_like(dz[:1], Cout, dz.shape[2], dz.shape[3])
+        with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
+            _check(lib.agr_sum_batch(_code(dz), _ptr(dz), _ptr(dzs), V, dzs.numel(), _stream(g)), "agr_sum_batch")
+        wt = torch.empty((Ca + Cb, Cout, k, k), dtype=w.dtype, device=w.device, memory_format=_CL)
+        with torch.cuda.device(g.device), stats.stage("styleunet_weight", launches=1):
+            _check(lib.agr_weight_flip_transpose(_ptr(w), _ptr(wt), Cout, Ca + Cb, k, _stream(g)), "agr_weight_flip_transpose")
+        da = _tc_conv(dz, wt[:Ca], Ca, k, None, None, None, False) if ctx.needs_input_grad[0] else None
+        dbb = _tc_conv(dzs, wt[Ca:], Cb, k, None, None, None, False) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[2]:
+            pad = [k // 2, k // 2]
+            dwa = torch.ops.aten.convolution_backward(dz, a, w[:, :Ca], None, [1, 1], pad, [1, 1], False, [0, 0], 1, [False, True, False])[1]
+            dwb = torch.ops.aten.convolution_backward(dzs, b, w[:, Ca:], None, [1, 1], pad, [1, 1], False, [0, 0], 1, [False, True, False])[1]
+            dw = torch.cat([dwa, dwb], 1).contiguous(memory_format=_CL)
+        return da, dbb, dw, (db.view(bshape) if has_b else None), None
+
+
+def equal_conv2d_split(a, b, weight, scale, act_bias=None, activate=True):
+    """ConvLayer on cat([a, b], 1) where b (batch 1) is shared by the batch of a; falls back to the plain path when the
+    shapes are outside the tensor-core kernel's coverage."""
+    Ca, Cb = a.shape[1], b.shape[1]
+    k = weight.shape[-1]
+    ok = (a.dtype == torch.bfloat16 and b.shape[0] == 1 and Ca % 64 == 0 and Cb % 64 == 0 and
+          _lib.load().agr_conv2d_tc_supported(a.shape[2], a.shape[3], Ca, weight.shape[0], k) and
+          _lib.load().agr_conv2d_tc_supported(a.shape[2], a.shape[3], Cb, weight.shape[0], k))
+    if not ok:
+        return equal_conv2d(torch.cat([a, expand_batch(b, a.shape[0])], 1), weight, scale, 1, k // 2, act_bias, activate)
+    w = _ModWeight.apply(weight, _ones(weight.shape[1], weight.device), scale, False, False, a.dtype)
+    return _SplitConvAct.apply(a, b, w, act_bias, activate)
 
 
 def equal_conv2d(x, weight, scale, stride, padding, act_bias=None, activate=True):

@@ -268,6 +268,9 @@ def main():
     wl.graph = graph
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
         return
 
     ms_step = ms / args.steps
@@ -299,6 +302,10 @@ def main():
         except Exception as e:  # the oracle is the checker; its absence must not hide the GPU number
             out["cpu_baseline"] = {"value": None, "unit": "views/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
     print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

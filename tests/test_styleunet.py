@@ -261,3 +261,25 @@ def test_bf16_network_tracks_fp32(built_lib):
     rel = lambda a, b: float((a - b).norm() / b.norm())
     assert rel(outs[1], outs[0]) < 3e-2, rel(outs[1], outs[0])
     assert rel(grads[1], grads[0]) < 8e-2, rel(grads[1], grads[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V,H,W,Ca,Cb,Cout", [(3, 16, 32, 128, 128, 128), (2, 32, 32, 64, 128, 64)])
+def test_split_contraction_equals_conv_of_concat(V, H, W, Ca, Cb, Cout, built_lib):
+    """conv(cat([a_v, b]), w) == conv(a_v, w[:, :Ca]) + conv(b, w[:, Ca:]) with b shared by the view batch."""
+    from animatablegaussians_b200 import styleunet_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bf = lambda t: t.to(torch.bfloat16)
+    a = bf(torch.randn(V, Ca, H, W, device="cuda", generator=g)).contiguous(memory_format=torch.channels_last)
+    b = bf(torch.randn(1, Cb, H, W, device="cuda", generator=g)).contiguous(memory_format=torch.channels_last)
+    w = bf(torch.randn(Cout, Ca + Cb, 3, 3, device="cuda", generator=g) / ((Ca + Cb) * 9) ** 0.5).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    a1, b1, w1, c1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    y1 = ops._SplitConvAct.apply(a1, b1, w1, c1, True)
+    a2, b2, w2, c2 = a.float().requires_grad_(True), b.float().requires_grad_(True), w.float().requires_grad_(True), bias.clone().requires_grad_(True)
+    y2 = torch.nn.functional.conv2d(torch.cat([a2, b2.expand(V, -1, -1, -1)], 1), w2, None, padding=1) + c2.view(1, -1, 1, 1)
+    y2 = torch.nn.functional.leaky_relu(y2, 0.2) * 2 ** 0.5
+    _cmp(y1, y2, 1.2e-2)
+    up = bf(torch.randn(y2.shape, device="cuda", generator=g))
+    y1.backward(up); y2.backward(up.float())
+    _cmp(a1.grad, a2.grad, 2e-2); _cmp(b1.grad, b2.grad, 2e-2); _cmp(w1.grad, w2.grad, 2e-2); _cmp(c1.grad, c2.grad, 2e-2)
