@@ -25,7 +25,8 @@ namespace tc {
 
 constexpr int TILE_W = 16, TILE_H = 8, BM = TILE_W * TILE_H;  // 128 pixels
 constexpr int BK = 64;                                       // channels per k-block (128 B of bf16)
-constexpr int STAGES = 3;                                    // 3 x 32 KB (BN=128): two CTAs per SM overlap epilogue and mainloop
+// pipeline depth is a template parameter: 4 stages when the grid is a single wave (1 CTA/SM anyway), 3 stages (96 KB at
+// BN=128) when there are more tiles than SMs so that two CTAs per SM overlap one's epilogue with the other's mainloop
 constexpr int A_BYTES = BM * BK * 2;                         // 16 KB
 constexpr int NUM_THREADS = 192;                             // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
 
@@ -98,14 +99,15 @@ struct ConvParams {
     const float* bias;     // (Cout) or null
     const float* noise;    // (H*W) or null
     const float* noise_w;  // (1) or null
-    const __nv_bfloat16* residual;  // (H, W, Cout) added before bias/activation, shared by the N images; or null
+    const float* residual;  // (H, W, Cout) fp32 added before bias/activation, shared by the N images; or null
+    float* y_f32;           // when set, the result is stored in fp32 here instead of bf16 in y (partial sums)
     int w_cin_offset;      // first input channel of the weight slice this call contracts with (split-K over a concat)
     int activate;
     __nv_bfloat16* y;      // (H, W, Cout)
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, (STAGES * (A_BYTES + BN * BK * 2) + 1024) * 2 <= 227 * 1024 ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, ConvParams p) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -186,7 +188,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const size_t pix = (size_t)h * p.W + w;   // noise is per pixel, shared by the N images
         const float add = (p.noise && p.noise_w) ? p.noise_w[0] * p.noise[pix] : 0.f;
         __nv_bfloat16* out = p.y + ((size_t)img * p.H * p.W + pix) * p.Cout + n0;
-        const __nv_bfloat16* res = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
+        const float* res = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
+        float* out32 = p.y_f32 ? p.y_f32 + ((size_t)img * p.H * p.W + pix) * p.Cout + n0 : nullptr;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -196,12 +199,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(packed);
             if (res) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) packed[i] = reinterpret_cast<const uint4*>(res + c0)[i];
+                for (int i = 0; i < 8; ++i) {
+                    const float4 rr = reinterpret_cast<const float4*>(res + c0)[i];
+                    r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + rr.x);
+                    r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + rr.y);
+                    r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + rr.z);
+                    r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + rr.w);
+                }
+            }
+            if (out32) {   // fp32 partial result (no epilogue math): consumed as `residual` by the second half
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    reinterpret_cast<float4*>(out32 + c0)[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                                           __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                continue;
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 float v0 = __uint_as_float(r[2 * i]) + add, v1 = __uint_as_float(r[2 * i + 1]) + add;
-                if (res) { const float2 rr = __bfloat1622float2(h2[i]); v0 += rr.x; v1 += rr.y; }
                 if (p.bias) { v0 += p.bias[n0 + c0 + 2 * i]; v1 += p.bias[n0 + c0 + 2 * i + 1]; }
                 if (p.activate) {
                     v0 = (v0 > 0.f ? v0 : 0.2f * v0) * 1.4142135623730951f;
@@ -279,20 +294,27 @@ static bool make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t 
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <int BN, int STAGES>
+static int launch_s(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, cudaStream_t s) {
+    constexpr int smem = STAGES * (A_BYTES + BN * BK * 2) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
+        attr = true;
+    }
+    dim3 grid(p.N * (p.H / TILE_H) * (p.W / TILE_W), p.Cout / BN);
+    conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, s>>>(mx, mw, p);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
 template <int BN>
 static int launch(const void* x, const void* w, const ConvParams& p, int w_cin_total, cudaStream_t s) {
     CUtensorMap mx, mw;
     if (!make_map_4d(&mx, x, (uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N, BK, TILE_W, TILE_H)) return AGR_ERR_CUDA;
     if (!make_map_3d(&mw, w, (uint64_t)w_cin_total, (uint64_t)p.taps, (uint64_t)p.Cout, BK, 1, BN)) return AGR_ERR_CUDA;
-    constexpr int smem = STAGES * (A_BYTES + BN * BK * 2) + 1024;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
-        attr = true;
-    }
-    dim3 grid(p.N * (p.H / TILE_H) * (p.W / TILE_W), p.Cout / BN);
-    conv_tc_kernel<BN><<<grid, NUM_THREADS, smem, s>>>(mx, mw, p);
-    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+    const long tiles = (long)p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN);
+    if (BN == 64 || tiles <= 148) return launch_s<BN, 4>(mx, mw, p, s);
+    return launch_s<BN, 3>(mx, mw, p, s);
 }
 
 }  // namespace tc
@@ -317,22 +339,24 @@ int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t N,
     ConvParams p;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
     p.bias = bias; p.noise = noise; p.noise_w = noise_w; p.activate = activate; p.y = static_cast<__nv_bfloat16*>(y);
-    p.residual = nullptr; p.w_cin_offset = 0;
+    p.residual = nullptr; p.y_f32 = nullptr; p.w_cin_offset = 0;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     if (Cout % 128 == 0) return launch<128>(x, w_krsc, p, Cin, s);
     return launch<64>(x, w_krsc, p, Cin, s);
 }
 
-int agr_conv2d_tc_forward_split(const void* x, const void* w_krsc, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                                int32_t ksize, int32_t w_cin_total, int32_t w_cin_offset, const void* residual, const float* bias,
-                                int32_t activate, void* cuda_stream) {
+int agr_conv2d_tc_forward_split(const void* x, const void* w_krsc, void* y, int32_t out_fp32, int32_t N, int32_t H, int32_t W,
+                                int32_t Cin, int32_t Cout, int32_t ksize, int32_t w_cin_total, int32_t w_cin_offset,
+                                const float* residual, const float* bias, int32_t activate, void* cuda_stream) {
     using namespace agr::tc;
     if (!x || !w_krsc || !y || N < 1 || !agr_conv2d_tc_supported(H, W, Cin, Cout, ksize)) return AGR_ERR_INVALID_ARGUMENT;
     if (w_cin_offset < 0 || (w_cin_offset % BK) || w_cin_offset + Cin > w_cin_total) return AGR_ERR_INVALID_ARGUMENT;
     ConvParams p;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
-    p.bias = bias; p.noise = nullptr; p.noise_w = nullptr; p.activate = activate; p.y = static_cast<__nv_bfloat16*>(y);
-    p.residual = static_cast<const __nv_bfloat16*>(residual); p.w_cin_offset = w_cin_offset;
+    p.bias = bias; p.noise = nullptr; p.noise_w = nullptr; p.activate = activate;
+    p.y = out_fp32 ? nullptr : static_cast<__nv_bfloat16*>(y);
+    p.y_f32 = out_fp32 ? static_cast<float*>(y) : nullptr;
+    p.residual = residual; p.w_cin_offset = w_cin_offset;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     if (Cout % 128 == 0) return launch<128>(x, w_krsc, p, w_cin_total, s);
     return launch<64>(x, w_krsc, p, w_cin_total, s);

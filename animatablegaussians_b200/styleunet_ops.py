@@ -38,7 +38,7 @@ _lib.register_symbols({
     "agr_conv2d_tc_forward": (C.c_int, [_p, _p, _p] + [C.c_int32] * 6 + [_p, _p, _p, C.c_int32, _p]),
     "agr_weight_flip_transpose": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
     "agr_sum_batch": (C.c_int, [C.c_int32, _p, _p, C.c_int32, C.c_int64, _p]),
-    "agr_conv2d_tc_forward_split": (C.c_int, [_p, _p, _p] + [C.c_int32] * 8 + [_p, _p, C.c_int32, _p]),
+    "agr_conv2d_tc_forward_split": (C.c_int, [_p, _p, _p] + [C.c_int32] * 9 + [_p, _p, C.c_int32, _p]),
 })
 
 _COMPUTE_DTYPE = torch.float32
@@ -387,11 +387,12 @@ class _ConvAct(torch.autograd.Function):
         return dx, dw, (db.view(bshape) if has_b else None), None, (dn.view(nshape) if has_n else None), None
 
 
-def _tc_conv_split(x, w, Cout, k, cin_total, cin_offset, residual, bias, activate):
+def _tc_conv_split(x, w, Cout, k, cin_total, cin_offset, residual, bias, activate, out_fp32=False):
     lib = _lib.load()
-    y = _new_like(x, Cout, x.shape[2], x.shape[3])
+    y = torch.empty((x.shape[0], Cout, x.shape[2], x.shape[3]), dtype=torch.float32 if out_fp32 else x.dtype, device=x.device,
+                    memory_format=_CL)
     with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=1):
-        _check(lib.agr_conv2d_tc_forward_split(_ptr(x), _ptr(w), _ptr(y), x.shape[0], x.shape[2], x.shape[3], x.shape[1], Cout, k,
+        _check(lib.agr_conv2d_tc_forward_split(_ptr(x), _ptr(w), _ptr(y), int(out_fp32), x.shape[0], x.shape[2], x.shape[3], x.shape[1], Cout, k,
                                                cin_total, cin_offset, _ptr(residual), _ptr(bias), int(activate), _stream(x)),
                "agr_conv2d_tc_forward_split")
     return y
@@ -407,7 +408,7 @@ class _SplitConvAct(torch.autograd.Function):
         w = w.contiguous(memory_format=_CL)
         Cout, k, Ca, Cb = w.shape[0], w.shape[-1], a.shape[1], b.shape[1]
         bb = bias.detach().float().contiguous() if bias is not None else None
-        zb = _tc_conv_split(b, w, Cout, k, Ca + Cb, Ca, None, None, False)
+        zb = _tc_conv_split(b, w, Cout, k, Ca + Cb, Ca, None, None, False, out_fp32=True)   # fp32 partial sum
         y = _tc_conv_split(a, w, Cout, k, Ca + Cb, 0, zb, bb, activate)
         ctx.save_for_backward(a, b, w, y if activate else None)
         ctx.meta = (activate, k, bias is not None, None if bias is None else bias.shape)

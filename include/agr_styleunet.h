@@ -76,13 +76,15 @@ int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t N,
                           int32_t Cout, int32_t ksize, const float* bias, const float* noise, const float* noise_w,
                           int32_t activate, void* cuda_stream);
 /* Same kernel contracting x (N,H,W,Cin) with the input-channel SLICE [w_cin_offset, w_cin_offset+Cin) of a wider weight
- * (Cout,k,k,w_cin_total) and adding `residual` (H,W,Cout) bf16 (shared by the N images) before bias / activation:
+ * (Cout,k,k,w_cin_total) and adding `residual` (H,W,Cout) fp32 (shared by the N images) before bias / activation;
+ * out_fp32 != 0 stores the raw fp32 accumulator in y (N,H,W,Cout fp32) — the partial sum the second half consumes:
  *   conv(cat([a_v, b]), w) = conv(a_v, w[.., :Ca]) + conv(b, w[.., Ca:])
  * so the skip concatenation of the colour-net tail (dual_styleunet.py:875-876) never materialises and the
  * view-independent half is computed once for all V views. */
-int agr_conv2d_tc_forward_split(const void* x, const void* w_krsc, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin,
-                                int32_t Cout, int32_t ksize, int32_t w_cin_total, int32_t w_cin_offset,
-                                const void* residual, const float* bias, int32_t activate, void* cuda_stream);
+int agr_conv2d_tc_forward_split(const void* x, const void* w_krsc, void* y, int32_t out_fp32, int32_t N, int32_t H,
+                                int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t w_cin_total,
+                                int32_t w_cin_offset, const float* residual, const float* bias, int32_t activate,
+                                void* cuda_stream);
 
 /* y[i] = sum_v x[v][i], i < n  (fp32 accumulate): the adjoint of broadcasting the shared colour-net prefix state to the
  * V views of a batch (ATen's strided reduction reaches ~0.3 TB/s on this shape; this streams at HBM rate). */
