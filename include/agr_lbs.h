@@ -45,6 +45,13 @@ int agr_lbs_points(int32_t N, int32_t J, const float* weights, const float* jnt_
                    const float* xyz_in, const float* vec_in, float* xyz_out, float* vec_out,
                    void* cuda_stream);
 
+/* SMPL-X joint chain (smplx/lbs.py:300-336 batch_rodrigues + :349-405 batch_rigid_transform), batch 1.
+ *   pose: (J,3) axis-angle, or (J,9) rotation matrices when pose_is_rotmat != 0; joints (J,3) rest joints;
+ *   parents (J) int32 kinematic tree (parents[0] ignored).  Outputs: rot_mats_out (J,9) or NULL,
+ *   posed_joints (J,3), A (J,4,4) relative transforms (what dataset_mv_rgb.py:172 turns into cano2live_jnt_mats). */
+int agr_smpl_joint_chain(int32_t J, const float* pose, int32_t pose_is_rotmat, const float* joints, const int32_t* parents,
+                         float* rot_mats_out, float* posed_joints, float* A, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
