@@ -353,6 +353,79 @@ __global__ void __launch_bounds__(256) sum_batch_kernel(const T* __restrict__ x,
     }
 }
 
+// ------------------------------------------------------------------------------------------------ bilinear 2x (+ add)
+// PyTorch's align_corners=False source index: max(0.5 * (dst + 0.5) - 0.5, 0); x1 = min(x0 + 1, in - 1).
+__device__ __forceinline__ void bil_src(int dst, int in, int& i0, int& i1, float& lam) {
+    const float src = fmaxf(0.5f * ((float)dst + 0.5f) - 0.5f, 0.f);
+    i0 = (int)src;
+    i1 = min(i0 + 1, in - 1);
+    lam = src - (float)i0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear2x_add_kernel(const float* __restrict__ vf, const T* __restrict__ base, T* __restrict__ y,
+                                                            int V, int Vb, int h, int w, int C) {
+    constexpr int VN = 4;   // 4 channels per thread (float4 of vf)
+    const int H = 2 * h, W = 2 * w, cv = C / VN;
+    const int64_t total = (int64_t)V * H * W * cv;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % cv) * VN;
+    int64_t p = idx / cv;
+    const int ox = (int)(p % W); p /= W;
+    const int oy = (int)(p % H);
+    const int v = (int)(p / H);
+    int y0, y1, x0, x1; float ly, lx;
+    bil_src(oy, h, y0, y1, ly);
+    bil_src(ox, w, x0, x1, lx);
+    const float* f = vf + (int64_t)v * h * w * C + c;
+    const float4 a = *reinterpret_cast<const float4*>(f + ((int64_t)y0 * w + x0) * C);
+    const float4 b = *reinterpret_cast<const float4*>(f + ((int64_t)y0 * w + x1) * C);
+    const float4 cc = *reinterpret_cast<const float4*>(f + ((int64_t)y1 * w + x0) * C);
+    const float4 d = *reinterpret_cast<const float4*>(f + ((int64_t)y1 * w + x1) * C);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    float r[4] = {w00 * a.x + w01 * b.x + w10 * cc.x + w11 * d.x, w00 * a.y + w01 * b.y + w10 * cc.y + w11 * d.y,
+                  w00 * a.z + w01 * b.z + w10 * cc.z + w11 * d.z, w00 * a.w + w01 * b.w + w10 * cc.w + w11 * d.w};
+    const int64_t pix = ((int64_t)oy * W + ox) * C + c;
+    const T* bp = base + (Vb == 1 ? 0 : (int64_t)v * H * W * C) + pix;
+    T* yp = y + (int64_t)v * H * W * C + pix;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) yp[i] = from_f<T>(to_f(from_f<T>(r[i])) + to_f(bp[i]));   // resize result rounds to T first, like .to(dtype)
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear2x_bwd_kernel(const T* __restrict__ g, float* __restrict__ d_vf, int V, int h, int w, int C) {
+    constexpr int VN = 4;
+    const int H = 2 * h, W = 2 * w, cv = C / VN;
+    const int64_t total = (int64_t)V * h * w * cv;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % cv) * VN;
+    int64_t p = idx / cv;
+    const int sx = (int)(p % w); p /= w;
+    const int sy = (int)(p % h);
+    const int v = (int)(p / h);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const T* gv = g + (int64_t)v * H * W * C + c;
+    for (int oy = max(2 * sy - 1, 0); oy <= min(2 * sy + 2, H - 1); ++oy) {
+        int y0, y1; float ly;
+        bil_src(oy, h, y0, y1, ly);
+        const float wy = (y0 == sy ? 1.f - ly : 0.f) + (y1 == sy ? ly : 0.f);
+        if (wy == 0.f) continue;
+        for (int ox = max(2 * sx - 1, 0); ox <= min(2 * sx + 2, W - 1); ++ox) {
+            int x0, x1; float lx;
+            bil_src(ox, w, x0, x1, lx);
+            const float wx = (x0 == sx ? 1.f - lx : 0.f) + (x1 == sx ? lx : 0.f);
+            if (wx == 0.f) continue;
+            const T* gp = gv + ((int64_t)oy * W + ox) * C;
+            const float ww = wy * wx;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += ww * to_f(gp[i]);
+        }
+    }
+    *reinterpret_cast<float4*>(d_vf + (((int64_t)v * h + sy) * w + sx) * C + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
 inline int grid_for(int64_t total, int block = 256) { return (int)((total + block - 1) / block); }
 
 }  // namespace agr
@@ -459,6 +532,25 @@ int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx
         if (vec) bias_act_bwd_kernel<float, true><<<(unsigned)blocks, 256, smem, s>>>((const float*)dy, (const float*)y, (float*)dx, pixels, C, noise, noise_period, d_bias, d_noise_w, activate, ppb);
         else bias_act_bwd_kernel<float, false><<<(unsigned)blocks, 256, smem, s>>>((const float*)dy, (const float*)y, (float*)dx, pixels, C, noise, noise_period, d_bias, d_noise_w, activate, ppb);
     }
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_bilinear2x_add_forward(int32_t dtype, const float* vf, const void* base, void* y, int32_t V, int32_t Vb, int32_t h, int32_t w,
+                               int32_t C, void* cuda_stream) {
+    if (!vf || !base || !y || V < 1 || (Vb != 1 && Vb != V) || h < 1 || w < 1 || C < 4 || (C % 4)) return AGR_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const int g = grid_for((int64_t)V * 4 * h * w * (C / 4));
+    if (dtype == AGR_BF16) bilinear2x_add_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(vf, (const __nv_bfloat16*)base, (__nv_bfloat16*)y, V, Vb, h, w, C);
+    else bilinear2x_add_kernel<float><<<g, 256, 0, s>>>(vf, (const float*)base, (float*)y, V, Vb, h, w, C);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_bilinear2x_backward(int32_t dtype, const void* g, float* d_vf, int32_t V, int32_t h, int32_t w, int32_t C, void* cuda_stream) {
+    if (!g || !d_vf || V < 1 || h < 1 || w < 1 || C < 4 || (C % 4)) return AGR_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const int gr = grid_for((int64_t)V * h * w * (C / 4));
+    if (dtype == AGR_BF16) bilinear2x_bwd_kernel<__nv_bfloat16><<<gr, 256, 0, s>>>((const __nv_bfloat16*)g, d_vf, V, h, w, C);
+    else bilinear2x_bwd_kernel<float><<<gr, 256, 0, s>>>((const float*)g, d_vf, V, h, w, C);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 

@@ -15,11 +15,18 @@ import torch
 ENABLED = False
 _events = {}
 _launches = 0
+_work = {}
 
 
 def reset():
-    global ENABLED, _events, _launches
-    ENABLED, _events, _launches = True, {}, 0
+    global ENABLED, _events, _launches, _work
+    ENABLED, _events, _launches, _work = True, {}, 0, {}
+
+
+def add_work(name, amount):
+    """Algorithmic work (FLOPs or bytes) of the call being timed under stage `name`."""
+    if ENABLED:
+        _work[name] = _work.get(name, 0.0) + float(amount)
 
 
 def count(n):
@@ -46,13 +53,28 @@ def stage(name, launches=0):
 def snapshot():
     global ENABLED
     torch.cuda.synchronize()
-    out = {"launches": _launches, "stages": {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in _events.items()}}
+    out = {"launches": _launches, "stages": {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in _events.items()},
+           "work": dict(_work)}
     ENABLED = False
     return out
 
 
 def stage_ms(st, steps):
     return {k: round(ms / steps, 4) for k, (ms, n) in st["stages"].items()}
+
+
+def roofline_tensor(st, steps, peaks):
+    """Tensor-pipe roofline of the tcgen05 implicit-GEMM convolution launches of one step."""
+    peak = peaks.get("bf16_tflops_sustained")
+    which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+    if not peak:
+        peak, which = 1400.0, "fallback (B200_PROFILING.md sustained)"
+    ms, n = st["stages"].get("styleunet_conv_tc", (0.0, 0))
+    fl = st.get("work", {}).get("styleunet_conv_tc", 0.0)
+    ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+    return {"bound": "tensor", "kernel": "conv_tc_kernel<BN,STAGES> (tcgen05.mma implicit-GEMM 3x3/1x1 conv, fwd + dgrad launches)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": which,
+            "launches_per_step": n / max(steps, 1), "algorithmic_flop_per_step": fl / max(steps, 1), "seconds_per_step": ms * 1e-3 / max(steps, 1)}
 
 
 def roofline(st, steps, views_local, P, W, H, peaks):
@@ -66,5 +88,8 @@ def roofline(st, steps, views_local, P, W, H, peaks):
     achieved = bytes_step / t_raster / 1e9 if t_raster > 0 else 0.0
     return {"bound": "hbm", "kernel": "rasterizer fwd+bwd launches of one step (preprocess, duplicate, CUB scan/sort, "
             "gather, blend fwd, blend bwd, preprocess bwd)", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-            "frac": achieved / hbm, "traffic": None, "peak_source": which,
+            "frac": achieved / hbm,
+            # dram__bytes_read.sum + dram__bytes_write.sum of the two blend kernels (the stage's dominant launches) for a
+            # 16-view step, from profiles/r01_ncu_full_blend_{fwd,bwd}.txt (ncu --set full, scene of tools/prof_raster.py)
+            "traffic": (506.76e6 + 375.75e6 + 774.91e6 + 196.65e6) * views_local / 16.0, "peak_source": which,
             "algorithmic_bytes_per_step": bytes_step, "seconds_per_step": t_raster}

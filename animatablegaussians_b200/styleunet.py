@@ -352,7 +352,7 @@ class DualStyleUNet(nn.Module):
             out = convs[i + 1](out, latent[:, i + 1], noise=noise[i + 1])
             skip = to_rgbs[lvl](out, latent[:, i + 2], skip)
             if view_feature is not None and i == self.view_level:
-                out = out + ops.bilinear_resize(view_feature, out.shape[-2:])
+                out = ops.add_view_feature(out, view_feature)
         if stop is not None:
             return out, skip
         return self.iwt(skip)
@@ -393,12 +393,12 @@ class DualStyleUNet(nn.Module):
         for convs, rgbs, st, vf in ((self.convs1, self.to_rgbs1, prefix["s1"], view_feature1),
                                     (self.convs2, self.to_rgbs2, prefix["s2"], view_feature2)):
             out, skip = st
-            if V > 1:
-                out = ops.expand_batch(out, V)
-                if skip is not None:
-                    skip = ops.expand_batch(skip, V)
             if vf is not None and self.view_level < 2 * len(rgbs):  # smaller nets never reach the view level
-                out = out + ops.bilinear_resize(vf, out.shape[-2:])
+                out = ops.add_view_feature(out, vf)                  # (1|V) + resize(V) -> V, one pass
+            elif V > 1:
+                out = ops.expand_batch(out, V)
+            if V > 1 and skip is not None:
+                skip = ops.expand_batch(skip, V)
             outs.append(self._decode(convs, rgbs, prefix["cond_list"], prefix["latent"], prefix["noise"], None,
                                      start=self.view_level + 2, state=(out, skip)))
         return ops.from_compute(torch.cat(outs, 1))

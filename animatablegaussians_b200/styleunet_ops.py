@@ -38,6 +38,8 @@ _lib.register_symbols({
     "agr_conv2d_tc_forward": (C.c_int, [_p, _p, _p] + [C.c_int32] * 6 + [_p, _p, _p, C.c_int32, _p]),
     "agr_weight_flip_transpose": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
     "agr_sum_batch": (C.c_int, [C.c_int32, _p, _p, C.c_int32, C.c_int64, _p]),
+    "agr_bilinear2x_add_forward": (C.c_int, [C.c_int32, _p, _p, _p] + [C.c_int32] * 5 + [_p]),
+    "agr_bilinear2x_backward": (C.c_int, [C.c_int32, _p, _p] + [C.c_int32] * 4 + [_p]),
     "agr_conv2d_tc_forward_split": (C.c_int, [_p, _p, _p] + [C.c_int32] * 9 + [_p, _p, C.c_int32, _p]),
 })
 
@@ -268,6 +270,50 @@ def bias_act(x, bias=None, noise=None, noise_weight=None, activate=True):
     return _BiasAct.apply(x, bias, noise, noise_weight, activate)
 
 
+class _AddViewFeature(torch.autograd.Function):
+    """out + bilinear_2x(view_feature) (dual_styleunet.py:881-883) in one pass; out may be the shared (batch-1) state."""
+
+    @staticmethod
+    def forward(ctx, base, vf):
+        lib = _lib.load()
+        base = _nhwc(base)
+        vf32 = vf.detach().float().contiguous(memory_format=_CL)
+        V, Cc, h, w = vf32.shape
+        y = torch.empty((V, Cc, 2 * h, 2 * w), dtype=base.dtype, device=base.device, memory_format=_CL)
+        with torch.cuda.device(base.device), stats.stage("styleunet_act", launches=1):
+            _check(lib.agr_bilinear2x_add_forward(_code(base), _ptr(vf32), _ptr(base), _ptr(y), V, base.shape[0], h, w, Cc, _stream(base)),
+                   "agr_bilinear2x_add_forward")
+        ctx.meta = (base.shape[0], V, Cc, h, w, vf.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        Vb, V, Cc, h, w, vdt = ctx.meta
+        g = _nhwc(g)
+        d_base = d_vf = None
+        if ctx.needs_input_grad[0]:
+            if Vb == V:
+                d_base = g
+            else:
+                d_base = _new_like(g[:1], Cc, 2 * h, 2 * w)
+                with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
+                    _check(lib.agr_sum_batch(_code(g), _ptr(g), _ptr(d_base), V, d_base.numel(), _stream(g)), "agr_sum_batch")
+        if ctx.needs_input_grad[1]:
+            d_vf = torch.empty((V, Cc, h, w), dtype=torch.float32, device=g.device, memory_format=_CL)
+            with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
+                _check(lib.agr_bilinear2x_backward(_code(g), _ptr(g), _ptr(d_vf), V, h, w, Cc, _stream(g)), "agr_bilinear2x_backward")
+            d_vf = d_vf.to(vdt)
+        return d_base, d_vf
+
+
+def add_view_feature(out, vf):
+    """out (1 or V, C, H, W) + F.interpolate(vf (V, C, H/2, W/2), (H, W), mode='bilinear')  ->  (V, C, H, W)."""
+    if out.shape[2] == 2 * vf.shape[2] and out.shape[3] == 2 * vf.shape[3] and vf.shape[1] % 8 == 0 and out.shape[0] in (1, vf.shape[0]):
+        return _AddViewFeature.apply(out, vf)
+    return expand_batch(out, vf.shape[0]) + bilinear_resize(vf, out.shape[-2:])
+
+
 def bilinear_resize(x, size):
     """F.interpolate(mode='bilinear') of the view feature (dual_styleunet.py:882,901)."""
     return F.interpolate(x.float(), size, mode="bilinear").to(_COMPUTE_DTYPE).contiguous(memory_format=_CL)
@@ -329,6 +375,7 @@ def _tc_conv(x, w, Cout, k, bias, noise, noise_w, activate):
     """x (1,Cin,H,W) NHWC bf16, w (Cout,Cin,k,k) KRSC bf16 -> (1,Cout,H,W) NHWC bf16 on tcgen05."""
     lib = _lib.load()
     y = _new_like(x, Cout, x.shape[2], x.shape[3])
+    stats.add_work("styleunet_conv_tc", 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * x.shape[1] * Cout * k * k)
     with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=1):
         _check(lib.agr_conv2d_tc_forward(_ptr(x), _ptr(w), _ptr(y), x.shape[0], x.shape[2], x.shape[3], x.shape[1], Cout, k, _ptr(bias),
                                          _ptr(noise), _ptr(noise_w), int(activate), _stream(x)), "agr_conv2d_tc_forward")
@@ -391,6 +438,7 @@ def _tc_conv_split(x, w, Cout, k, cin_total, cin_offset, residual, bias, activat
     lib = _lib.load()
     y = torch.empty((x.shape[0], Cout, x.shape[2], x.shape[3]), dtype=torch.float32 if out_fp32 else x.dtype, device=x.device,
                     memory_format=_CL)
+    stats.add_work("styleunet_conv_tc", 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * x.shape[1] * Cout * k * k)
     with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=1):
         _check(lib.agr_conv2d_tc_forward_split(_ptr(x), _ptr(w), _ptr(y), int(out_fp32), x.shape[0], x.shape[2], x.shape[3], x.shape[1], Cout, k,
                                                cin_total, cin_offset, _ptr(residual), _ptr(bias), int(activate), _stream(x)),

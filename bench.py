@@ -282,6 +282,7 @@ def main():
     except Exception:
         pass
     roof = stats.roofline(st, args.steps, len(wl.views), wl.P, IMG, IMG, peaks)
+    roof_tc = stats.roofline_tensor(st, args.steps, peaks)
     out = {
         "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -294,7 +295,7 @@ def main():
                    "l2": "step working set (activations, maps, instance streams: several GB) exceeds the 126 MB L2; no explicit flush",
                    "library_ops": list(__import__("animatablegaussians_b200.styleunet_ops", fromlist=["x"]).LIBRARY_OPS)},
         "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes},
-        "gpu_launches": st["launches"], "clocks": clocks, "roofline": roof, "stage_ms_per_step": stats.stage_ms(st, args.steps),
+        "gpu_launches": st["launches"], "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tc, "stage_ms_per_step": stats.stage_ms(st, args.steps),
     }
     if not args.no_cpu_baseline:
         try:

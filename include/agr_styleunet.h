@@ -86,6 +86,16 @@ int agr_conv2d_tc_forward_split(const void* x, const void* w_krsc, void* y, int3
                                 int32_t w_cin_offset, const float* residual, const float* bias, int32_t activate,
                                 void* cuda_stream);
 
+/* View-feature injection of the colour net (dual_styleunet.py:881-883,900-902):
+ *   y[v] = base[v or 0] + bilinear_2x(vf[v])      F.interpolate(mode='bilinear', align_corners=False), exact 2x
+ * vf (V,h,w,C) fp32 NHWC, base (Vb,2h,2w,C) dtype NHWC with Vb in {1,V}, y (V,2h,2w,C) dtype.  One pass instead of the
+ * reference's resize -> add (two full-resolution fp32 intermediates per view).  The backward w.r.t. vf is the adjoint
+ * resampling of g (V,2h,2w,C) dtype into d_vf (V,h,w,C) fp32, gather form (no atomics). */
+int agr_bilinear2x_add_forward(int32_t dtype, const float* vf, const void* base, void* y, int32_t V, int32_t Vb, int32_t h,
+                               int32_t w, int32_t C, void* cuda_stream);
+int agr_bilinear2x_backward(int32_t dtype, const void* g, float* d_vf, int32_t V, int32_t h, int32_t w, int32_t C,
+                            void* cuda_stream);
+
 /* y[i] = sum_v x[v][i], i < n  (fp32 accumulate): the adjoint of broadcasting the shared colour-net prefix state to the
  * V views of a batch (ATen's strided reduction reaches ~0.3 TB/s on this shape; this streams at HBM rate). */
 int agr_sum_batch(int32_t dtype, const void* x, void* y, int32_t V, int64_t n, void* cuda_stream);

@@ -283,3 +283,23 @@ def test_split_contraction_equals_conv_of_concat(V, H, W, Ca, Cb, Cout, built_li
     up = bf(torch.randn(y2.shape, device="cuda", generator=g))
     y1.backward(up); y2.backward(up.float())
     _cmp(a1.grad, a2.grad, 2e-2); _cmp(b1.grad, b2.grad, 2e-2); _cmp(w1.grad, w2.grad, 2e-2); _cmp(c1.grad, c2.grad, 2e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1.2e-2)])
+@pytest.mark.parametrize("V,Vb", [(3, 1), (2, 2)])
+def test_add_view_feature_matches_interpolate(V, Vb, dtype, tol, built_lib):
+    """out + F.interpolate(vf, 2x, 'bilinear') fused, incl. the adjoint resampling, vs ATen in float64."""
+    from animatablegaussians_b200 import styleunet_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(6)
+    vf = torch.randn(V, 16, 12, 10, device="cuda", generator=g)
+    base = torch.randn(Vb, 16, 24, 20, device="cuda", generator=g).to(dtype)
+    va, ba = vf.clone().requires_grad_(True), base.clone().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ya = ops.add_view_feature(ba, va)
+    vb, bb = vf.double().requires_grad_(True), base.double().requires_grad_(True)
+    yb = bb + torch.nn.functional.interpolate(vb, (24, 20), mode="bilinear")
+    _cmp(ya, yb, tol)
+    up = torch.randn(yb.shape, device="cuda", generator=g).to(dtype)
+    ya.backward(up); yb.backward(up.double())
+    _cmp(va.grad, vb.grad, tol)
+    _cmp(ba.grad, bb.grad, 2 * tol)
