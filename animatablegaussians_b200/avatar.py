@@ -20,10 +20,55 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import camera, lbs
+import ctypes as C
+
+from . import _lib, camera, lbs, stats
 from . import styleunet_ops as ops
 from .rasterizer import GaussianRasterizer, rasterize_gaussians_batched
 from .styleunet import DualStyleUNet
+
+
+_lib.register_symbols({
+    "agr_gather_maps_forward": (C.c_int, [C.c_int32] + [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
+    "agr_gather_maps_backward": (C.c_int, [C.c_int32] + [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
+})
+
+
+class _GatherMaps(torch.autograd.Function):
+    """(front, back) NHWC decoder outputs (V,C,S,S) -> (V,N,C) fp32 at the canonical-mask pixels (agr_avatar.h)."""
+
+    @staticmethod
+    def forward(ctx, front, back, half, pix):
+        lib = _lib.load()
+        front, back = ops._nhwc(front), ops._nhwc(back)
+        V, Cc, S, _ = front.shape
+        N = half.shape[0]
+        out = torch.empty((V, N, Cc), dtype=torch.float32, device=front.device)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(front.device), stats.stage("avatar_gather", launches=1):
+            st = lib.agr_gather_maps_forward(ops._code(front), p(front), p(back), p(half), p(pix), p(out), V, S, Cc, N,
+                                             C.c_void_p(torch.cuda.current_stream(front.device).cuda_stream))
+        if st != _lib.AGR_OK:
+            raise RuntimeError("agr_gather_maps_forward failed: %d" % st)
+        ctx.save_for_backward(half, pix)
+        ctx.meta = (V, Cc, S, N, front.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        half, pix = ctx.saved_tensors
+        V, Cc, S, N, dt = ctx.meta
+        g = g.float().contiguous()
+        df = torch.empty((V, Cc, S, S), dtype=dt, device=g.device, memory_format=torch.channels_last)
+        db = torch.empty_like(df)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(g.device), stats.stage("avatar_gather", launches=1):
+            st = lib.agr_gather_maps_backward(ops._code(df), p(g), p(half), p(pix), p(df), p(db), V, S, Cc, N,
+                                              C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream))
+        if st != _lib.AGR_OK:
+            raise RuntimeError("agr_gather_maps_backward failed: %d" % st)
+        return df, db, None, None
 
 
 def inverse_sigmoid(x):
@@ -138,6 +183,7 @@ class AvatarNet(nn.Module):
         rc = torch.nonzero(self.cano_smpl_mask)
         self._half = (rc[:, 1] >= size).long()
         self._pix = rc[:, 0] * size + (rc[:, 1] % size)
+        self._half32, self._pix32 = self._half.int().contiguous(), self._pix.int().contiguous()
         self._flat = rc[:, 0] * (2 * size) + rc[:, 1]
 
     @staticmethod
@@ -159,6 +205,11 @@ class AvatarNet(nn.Module):
             return m[self._half, :, self._pix]
         m = maps.reshape(maps.shape[0], 2, C, -1)
         return m[:, self._half, :, self._pix].permute(1, 0, 2).contiguous()   # advanced dims come first: (N,V,C)
+
+    def _gather_pair(self, front, back):
+        """Decoder outputs (V,C,S,S) x2 (compute dtype, NHWC) -> (N,C) for V == 1 else (V,N,C); one fused gather."""
+        out = _GatherMaps.apply(front, back, self._half32, self._pix32)
+        return out[0] if out.shape[0] == 1 else out
 
     def _as_map(self, maps):
         front, back = torch.split(maps, [maps.shape[1] // 2] * 2, 1)
@@ -303,19 +354,24 @@ class AvatarNet(nn.Module):
             views = self.prepare_views(extrs, intrs, img_w, img_h, bg_color)
         V = views["V"]
         pose_map = items['smpl_pos_map'][:3]
-        cano_pts, pos_map = self.get_positions(pose_map, return_map=True)
-        opacity, scales, rotations = self.get_others(pose_map)
+        pf, pb = self.position_net.forward_maps([self.position_style], pose_map[None])
+        cano_pts = 0.05 * self._gather_pair(pf, pb) + self.cano_gaussian_model.get_xyz
+        pos_map = None   # (the (S,2S,3) map view is only produced by render(); the trainer reads it for visualisation)
+        of, ob = self.other_net.forward_maps([self.other_style], pose_map[None])
+        opacity, scales, rotations = self._activate_others(self._gather_pair(of, ob))
         nonrigid_offset = cano_pts - self.init_points
         if self.with_viewdirs:
             with torch.no_grad():
                 live = lbs.skin_points(self.lbs, items['cano2live_jnt_mats'], self.init_points, self.cano_nmls)
             prefix = self.color_net.forward_prefix([self._color_style()], pose_map[None])
             fv, bv = self.get_viewdir_feat_batched(live, views["cam_pos"])
-            colors = self._gather(self.color_net.forward_view_tail(prefix, fv, bv))
+            cf, cb = self.color_net.forward_view_tail(prefix, fv, bv, as_pair=True)
+            colors = self._gather_pair(cf, cb)
             if V == 1:
                 colors = colors[None]
         else:
-            colors, _ = self.get_colors(pose_map)
+            cf, cb = self.color_net.forward_maps([self._color_style()], pose_map[None])
+            colors = self._gather_pair(cf, cb)
         pos, rot = lbs.transform_cano2live(self.lbs, items['cano2live_jnt_mats'], cano_pts, rotations)
         color, radii, depth, alpha = rasterize_gaussians_batched(pos, None, None, colors, opacity, scales, rot, None,
                                                                  views["settings"])

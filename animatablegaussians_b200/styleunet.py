@@ -372,6 +372,15 @@ class DualStyleUNet(nn.Module):
         images = ops.from_compute(torch.cat([image1, image2], 1))
         return (images, latent) if return_latents else (images, None)
 
+    def forward_maps(self, styles, condition_img, view_feature1=None, view_feature2=None):
+        """forward() with the fixed noise buffers, returning the two decoder outputs (front, back) separately in the
+        compute dtype / NHWC — what AvatarNet's fused gather consumes (no channel cat, no fp32 NCHW copy)."""
+        latent = self._latent(styles, False, 1, None, None)
+        noise = [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
+        cond_list = self.encode(ops.to_compute(condition_img))
+        return (self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, view_feature1),
+                self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, view_feature2))
+
     # ------------------------------------------------------------------ view-batch split (exact)
     def forward_prefix(self, styles, condition_img):
         """Everything that does not depend on the view feature: encoder + both decoders up to and including
@@ -384,7 +393,7 @@ class DualStyleUNet(nn.Module):
         s2 = self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, None, stop=stop)
         return dict(latent=latent, noise=noise, cond_list=cond_list, s1=s1, s2=s2)
 
-    def forward_view_tail(self, prefix, view_feature1, view_feature2):
+    def forward_view_tail(self, prefix, view_feature1, view_feature2, as_pair=False):
         """View-dependent remainder for a BATCH of V views (view features (V,128,h,w)): add the (bilinearly resized)
         view feature to the shared prefix state, run the last decoder level(s) once with batch V — every layer's
         modulated weight is prepared once and shared by the V views."""
@@ -401,4 +410,6 @@ class DualStyleUNet(nn.Module):
                 skip = ops.expand_batch(skip, V)
             outs.append(self._decode(convs, rgbs, prefix["cond_list"], prefix["latent"], prefix["noise"], None,
                                      start=self.view_level + 2, state=(out, skip)))
+        if as_pair:
+            return outs[0], outs[1]
         return ops.from_compute(torch.cat(outs, 1))

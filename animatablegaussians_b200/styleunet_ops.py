@@ -87,9 +87,16 @@ def _check(st, what):
         raise RuntimeError("%s failed (status %d) %s" % (what, st, _lib.cuda_error_string() if st == _lib.AGR_ERR_CUDA else ""))
 
 
+_TRACE_COPIES = bool(int(__import__("os").environ.get("AGR_TRACE_COPIES", "0")))
+
+
 def _nhwc(x):
     if not x.is_cuda:
         raise RuntimeError("animatablegaussians_b200 StyleUNet operators are CUDA-only (no CPU fallback)")
+    if _TRACE_COPIES and x.ndim == 4 and not x.is_contiguous(memory_format=_CL) and x.numel() > (1 << 24):
+        import traceback
+        fr = [f for f in traceback.extract_stack(limit=6)][:-1]
+        print("[agr copy] %s %s strides=%s  <- %s" % (tuple(x.shape), x.dtype, x.stride(), " < ".join("%s:%d" % (f.name, f.lineno) for f in reversed(fr))))
     return x.contiguous(memory_format=_CL)
 
 

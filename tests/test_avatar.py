@@ -62,3 +62,22 @@ def test_train_step_updates_all_networks(built_lib):
     opt.step()
     assert torch.allclose(opt.flat_param[idx], expect, rtol=1e-4, atol=1e-7)
     assert float(opt.flat_grad.abs().max()) == 0.0
+
+
+def test_fused_gather_equals_reference_indexing(built_lib):
+    """_gather_pair (one kernel on the NHWC decoder outputs) == cat on W / permute / boolean-mask (avatar.py:95-97)."""
+    net, items, extrs, Ks, img = _setup(P=5000, size=128, V=1, img=64)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for V in (1, 3):
+        f = torch.randn(V, 8, 128, 128, device="cuda", generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        b = torch.randn(V, 8, 128, 128, device="cuda", generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        got = net._gather_pair(f, b)
+        up = torch.randn(got.shape, device="cuda", generator=g)
+        got.backward(up)
+        gf, gb = f.grad.clone(), b.grad.clone()
+        f.grad = None; b.grad = None
+        want = torch.stack([torch.cat([f[v:v + 1], b[v:v + 1]], 3)[0].permute(1, 2, 0)[net.cano_smpl_mask] for v in range(V)], 0)
+        want = want[0] if V == 1 else want
+        assert torch.equal(got, want)
+        want.backward(up)
+        assert torch.equal(gf, f.grad) and torch.equal(gb, b.grad)
