@@ -220,40 +220,25 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const T* __restrict__
     for (int i = 0; i < VN; ++i) bsum[i] = 0.f;
     float nsum = 0.f;
     if (my_lane < lanes) {
-        // 4 pixels per trip: all eight 128-bit loads are issued before the first use (memory-level parallelism; the
-        // kernel is a pure HBM stream: dy + y in, dx out)
-        constexpr int UNR = 4;
-        for (int64_t pb = p0 + my_lane; pb < p1; pb += (int64_t)lanes * UNR) {
-            float g[UNR][VN], o[UNR][VN];
-            bool ok[UNR];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int64_t p = pb + (int64_t)u * lanes;
-                ok[u] = p < p1;
-                if (!ok[u]) continue;
-                if (VECTOR) {
-                    unpack(*reinterpret_cast<const typename VecOf<T>::V*>(dy + p * C + my_c), g[u]);
-                    if (activate) unpack(*reinterpret_cast<const typename VecOf<T>::V*>(y + p * C + my_c), o[u]);
-                } else {
-                    g[u][0] = to_f(dy[p * C + my_c]);
-                    if (activate) o[u][0] = to_f(y[p * C + my_c]);
-                }
+        for (int64_t p = p0 + my_lane; p < p1; p += lanes) {
+            float g[VN], o[VN];
+            if (VECTOR) {
+                unpack(*reinterpret_cast<const typename VecOf<T>::V*>(dy + p * C + my_c), g);
+                if (activate) unpack(*reinterpret_cast<const typename VecOf<T>::V*>(y + p * C + my_c), o);
+            } else {
+                g[0] = to_f(dy[p * C + my_c]);
+                if (activate) o[0] = to_f(y[p * C + my_c]);
             }
+            float psum = 0.f;
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                if (!ok[u]) continue;
-                const int64_t p = pb + (int64_t)u * lanes;
-                float psum = 0.f;
-#pragma unroll
-                for (int i = 0; i < VN; ++i) {
-                    if (activate) g[u][i] *= (o[u][i] > 0.f ? kSqrt2 : 0.2f * kSqrt2);
-                    bsum[i] += g[u][i];
-                    psum += g[u][i];
-                }
-                if (noise) nsum += psum * noise[p % nper];
-                if (VECTOR) { typename VecOf<T>::V v; pack(g[u], v); *reinterpret_cast<typename VecOf<T>::V*>(dx + p * C + my_c) = v; }
-                else dx[p * C + my_c] = from_f<T>(g[u][0]);
+            for (int i = 0; i < VN; ++i) {
+                if (activate) g[i] *= (o[i] > 0.f ? kSqrt2 : 0.2f * kSqrt2);
+                bsum[i] += g[i];
+                psum += g[i];
             }
+            if (noise) nsum += psum * noise[p % nper];
+            if (VECTOR) { typename VecOf<T>::V v; pack(g, v); *reinterpret_cast<typename VecOf<T>::V*>(dx + p * C + my_c) = v; }
+            else dx[p * C + my_c] = from_f<T>(g[0]);
         }
         if (d_bias) {
 #pragma unroll
