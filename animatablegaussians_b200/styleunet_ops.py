@@ -24,7 +24,8 @@ from . import _lib, stats
 LIBRARY_OPS = ("conv2d wgrad, all shapes (cuDNN via torch)",
                "conv2d fwd/dgrad for stride-2, 8x8-resolution, Cin=3 and Cout in {12,32} layers (cuDNN via torch)",
                "conv_transpose2d fwd/dgrad/wgrad (cuDNN via torch)",
-               "viewdir_net 4x4 convs (cuDNN via torch)", "bilinear resize of the view feature (ATen)")
+               "viewdir_net 4x4 convs (cuDNN via torch)", "style / modulation EqualLinear GEMVs (cuBLAS via torch)",
+               "CUB DeviceScan + DeviceRadixSort in the rasterizer binning (as in the reference)")
 
 _p = C.c_void_p
 _lib.register_symbols({
