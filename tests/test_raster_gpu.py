@@ -153,3 +153,24 @@ def test_full_size_vs_reference(built_lib, ref_available):
         got = Hn.run_product(sc, up)
         rep = Hn.compare("full_v%d" % v, got, want, util.TOL, util.assert_close)
         print("full", v, {k: "%.1e" % e for k, e in rep.items()})
+
+
+def test_sync_free_mode_matches_and_flags_overflow(built_lib):
+    """num_rendered == NULL (device-resident count, padded sort, CUDA-graph capturable) renders the same image; a too
+    small capacity raises the device-side overflow flag instead of blocking."""
+    from animatablegaussians_b200 import rasterizer as R, synthetic as S, camera as C
+    P, V, img = 30000, 3, 256
+    g = S.make_gaussians(P, seed=5)
+    extrs, Ks = S.ring_cameras(V, img=img, focal=275.0)
+    T = lambda a: torch.from_numpy(a).cuda()
+    x, o, s, q, c = T(g["xyz"]), T(g["opacity"]), T(g["scales"]), T(g["rotations"]), T(g["rgb"])
+    bg = torch.zeros(3, device="cuda")
+    bs = C.make_batched_settings(extrs, Ks, img, img, bg, "cuda")
+    col0, rad0, dep0, alp0 = R.rasterize_gaussians_batched(x, None, None, c, o, s, q, None, bs)
+    need = max(R._capacity_hint.values())
+    col1, rad1, dep1, alp1 = R.rasterize_gaussians_batched(x, None, None, c, o, s, q, None, bs._replace(capacity=2 * need))
+    st = R.last_device_status
+    assert int(st[1]) == 0 and int(st[0]) > 0
+    assert torch.equal(col0, col1) and torch.equal(dep0, dep1) and torch.equal(alp0, alp1) and torch.equal(rad0, rad1)
+    R.rasterize_gaussians_batched(x, None, None, c, o, s, q, None, bs._replace(capacity=max(int(st[0]) // 4, 16)))
+    assert int(R.last_device_status[1]) == 1
