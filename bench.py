@@ -219,6 +219,15 @@ def cpu_baseline_sample(n_views=2):
                       "its CUDA ops and its Python cannot travel to the GPU box)" % n_views}
 
 
+def _exit_multi_rank():
+    """Leave without tearing NCCL down: the communicator is referenced by the captured CUDA graph, and
+    barrier()/destroy_process_group() after a graph-captured all-reduce was observed to hang (torch 2.11 / NCCL 2.28).
+    All collectives of the run have completed (device_time_ms ends with a barrier + synchronize)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,10 +277,7 @@ def main():
     wl.graph = graph
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
-        return
+        _exit_multi_rank()
 
     ms_step = ms / args.steps
     value = N_VIEWS / (ms_step * 1e-3)
@@ -304,9 +310,7 @@ def main():
             out["cpu_baseline"] = {"value": None, "unit": "views/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
     print(json.dumps(out))
     if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+        _exit_multi_rank()
 
 
 if __name__ == "__main__":
