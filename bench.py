@@ -303,7 +303,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes},
         "gpu_launches": st["launches"], "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tc, "stage_ms_per_step": stats.stage_ms(st, args.steps),
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only
         try:
             out["cpu_baseline"] = cpu_baseline_sample()
         except Exception as e:  # the oracle is the checker; its absence must not hide the GPU number
