@@ -23,11 +23,17 @@ template <typename T> struct VecOf;
 template <> struct VecOf<float> { static constexpr int N = 4; using V = float4; };
 template <> struct VecOf<__nv_bfloat16> { static constexpr int N = 8; using V = uint4; };
 
-__device__ __forceinline__ void unpack(const float4& v, float* f) { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
-__device__ __forceinline__ void unpack(const uint4& v, float* f) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+// Vectors are loaded BY VALUE through ld_vec (one LDG.128): unpacking through a reference to global memory lets the
+// compiler split the access into four 32-bit loads, which quarters the sector efficiency of every warp-level load.
+template <typename V> __device__ __forceinline__ V ld_vec(const void* p) { return __ldg(reinterpret_cast<const V*>(p)); }
+__device__ __forceinline__ void unpack(float4 v, float* f) { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+__device__ __forceinline__ void unpack(uint4 v, float* f) {
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    for (int i = 0; i < 4; ++i) {   // bf16 -> fp32 is a 16-bit shift
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
 }
 __device__ __forceinline__ void pack(const float* f, float4& v) { v = make_float4(f[0], f[1], f[2], f[3]); }
 __device__ __forceinline__ void pack(const float* f, uint4& v) {
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(256) upfirdn_kernel(const T* __restrict__ x, T
             const T* src = xn + ((int64_t)iy * W + ix) * C;
             if (VECTOR) {
                 float f[VN];
-                unpack(*reinterpret_cast<const typename VecOf<T>::V*>(src), f);
+                unpack(ld_vec<typename VecOf<T>::V>(src), f);
 #pragma unroll
                 for (int i = 0; i < VN; ++i) acc[i] += t * f[i];
             } else {
@@ -105,6 +111,65 @@ __global__ void __launch_bounds__(256) upfirdn_kernel(const T* __restrict__ x, T
         *reinterpret_cast<typename VecOf<T>::V*>(dst) = v;
     } else {
         dst[0] = from_f<T>(acc[0]);
+    }
+}
+
+// Blur (up = down = 1, K x K taps) on a channel-vectorisable tensor.  The one-pixel-per-thread kernel above issues K*K
+// vector loads + index arithmetic per output and is issue-bound (r01 ncu: ~1.1 TB/s at 16x1024x1024x16).  Here a
+// thread owns ROWS vertically adjacent outputs of one channel vector and walks the ROWS+K-1 input rows once: each
+// loaded vector feeds up to K outputs ((ROWS+K-1)*K/ROWS = 7 loads per output for K = ROWS = 4 instead of 16).
+// Every output still accumulates its taps in (ky, kx) ascending order, so results are bit-identical to upfirdn_kernel.
+template <typename T, int K, int ROWS>
+__global__ void __launch_bounds__(256) blur_strip_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C,
+                                                        int outH, int outW, FirParams fp) {
+    constexpr int VN = VecOf<T>::N;
+    using V = typename VecOf<T>::V;
+    const int cv = C / VN;
+    const int strips = (outH + ROWS - 1) / ROWS;
+    const int64_t total = (int64_t)N * strips * outW * cv;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % cv);
+    int64_t p = idx / cv;
+    const int ox = (int)(p % outW); p /= outW;
+    const int st = (int)(p % strips);
+    const int n = (int)(p / strips);
+    const int oy0 = st * ROWS;
+    float acc[ROWS][VN];
+#pragma unroll
+    for (int o = 0; o < ROWS; ++o)
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[o][i] = 0.f;
+    const int by = oy0 - fp.pad_y0, bx = ox - fp.pad_x0;
+    const T* xn = x + (int64_t)n * H * W * C + (int64_t)c * VN;
+#pragma unroll
+    for (int r = 0; r < ROWS + K - 1; ++r) {
+        const int iy = by + r;
+        if (iy < 0 || iy >= H) continue;
+        const T* xr = xn + (int64_t)iy * W * C;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            const int ix = bx + kx;
+            if (ix < 0 || ix >= W) continue;
+            float f[VN];
+            unpack(ld_vec<V>(xr + (int64_t)ix * C), f);
+#pragma unroll
+            for (int o = 0; o < ROWS; ++o) {
+                const int ky = r - o;   // compile-time after unrolling
+                if (ky < 0 || ky >= K) continue;
+                const float t = fp.taps[ky * K + kx];
+#pragma unroll
+                for (int i = 0; i < VN; ++i) acc[o][i] += t * f[i];
+            }
+        }
+    }
+    T* dst = y + (((int64_t)n * outH + oy0) * outW + ox) * C + (int64_t)c * VN;
+#pragma unroll
+    for (int o = 0; o < ROWS; ++o) {
+        if (oy0 + o >= outH) break;
+        V v;
+        pack(acc[o], v);
+        *reinterpret_cast<V*>(dst + (int64_t)o * outW * C) = v;
     }
 }
 
@@ -130,7 +195,7 @@ __global__ void __launch_bounds__(256) haar_kernel(const T* __restrict__ x, T* _
     float a[4][VN];  // image pixels (0,0) (0,1) (1,0) (1,1) or sub-bands ll lh hl hh
     using V = typename VecOf<T>::V;
     auto ld = [&](const T* ptr, float* f) {
-        if (VECTOR) unpack(*reinterpret_cast<const V*>(ptr), f); else f[0] = to_f(ptr[0]);
+        if (VECTOR) unpack(ld_vec<V>(ptr), f); else f[0] = to_f(ptr[0]);
     };
     auto st = [&](T* ptr, const float* f) {
         if (VECTOR) { V v; pack(f, v); *reinterpret_cast<V*>(ptr) = v; } else ptr[0] = from_f<T>(f[0]);
@@ -186,7 +251,7 @@ __global__ void __launch_bounds__(256) bias_act_fwd_kernel(const T* __restrict__
         const int64_t p = idx / cv;
         const float add = noise ? nw * noise[p % nper] : 0.f;
         float f[VN];
-        if (VECTOR) unpack(*reinterpret_cast<const typename VecOf<T>::V*>(x + p * C + c), f); else f[0] = to_f(x[p * C + c]);
+        if (VECTOR) unpack(ld_vec<typename VecOf<T>::V>(x + p * C + c), f); else f[0] = to_f(x[p * C + c]);
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
             float v = f[i] + add + (bias ? bias[c + i] : 0.f);
@@ -223,8 +288,8 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const T* __restrict__
         for (int64_t p = p0 + my_lane; p < p1; p += lanes) {
             float g[VN], o[VN];
             if (VECTOR) {
-                unpack(*reinterpret_cast<const typename VecOf<T>::V*>(dy + p * C + my_c), g);
-                if (activate) unpack(*reinterpret_cast<const typename VecOf<T>::V*>(y + p * C + my_c), o);
+                unpack(ld_vec<typename VecOf<T>::V>(dy + p * C + my_c), g);
+                if (activate) unpack(ld_vec<typename VecOf<T>::V>(y + p * C + my_c), o);
             } else {
                 g[0] = to_f(dy[p * C + my_c]);
                 if (activate) o[0] = to_f(y[p * C + my_c]);
@@ -334,6 +399,111 @@ __global__ void __launch_bounds__(256) modweight_bwd_kernel(const float* __restr
     }
 }
 
+// Shared-memory variants (rows of <= 12288 floats, 16-byte aligned): the (Cin,k,k) master-weight row is staged with
+// coalesced float4 loads issued back to back (one DRAM round trip instead of n/256 dependent ones), the strided
+// [ci*kk+t] accesses then hit shared memory (stride kk is odd or 1: conflict-free), and the backward builds the d_w
+// row in place and writes it back coalesced.  Same per-element arithmetic and reduction order as the kernels above.
+__device__ __forceinline__ void stage_row(const float* __restrict__ src, float* dst, int n4) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int base = 0; base < n4; base += 4 * 256) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int j = base + k * 256 + threadIdx.x; if (j < n4) v[k] = __ldg(s4 + j); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int j = base + k * 256 + threadIdx.x; if (j < n4) d4[j] = v[k]; }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) modweight_fwd_smem_kernel(const float* __restrict__ w, const float* __restrict__ s, float scale,
+                                                                int Cout, int Cin, int kk, int demodulate, int transpose_io,
+                                                                T* __restrict__ w_out, float* __restrict__ demod_out) {
+    extern __shared__ float4 s_row4[];
+    float* sw = reinterpret_cast<float*>(s_row4);
+    __shared__ float s_part[32];
+    __shared__ float s_demod;
+    const int co = blockIdx.x;
+    const int n = Cin * kk;
+    stage_row(w + (size_t)co * n, sw, n >> 2);
+    __syncthreads();
+    float d = 1.f;
+    if (demodulate) {
+        float acc = 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float u = scale * sw[i] * s[i / kk];
+            acc += u * u;
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.f;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (threadIdx.x == 0) { s_demod = rsqrtf(v + 1e-8f); if (demod_out) demod_out[co] = s_demod; }
+        }
+        __syncthreads();
+        d = s_demod;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int t = i / Cin, ci = i - t * Cin;
+        const float u = scale * sw[ci * kk + t] * s[ci] * d;
+        const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
+        w_out[o] = from_f<T>(u);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) modweight_bwd_smem_kernel(const float* __restrict__ w, const float* __restrict__ s, float scale,
+                                                                int Cout, int Cin, int kk, int demodulate, int transpose_io,
+                                                                const T* __restrict__ d_wout, const float* __restrict__ demod,
+                                                                float* __restrict__ d_w, float* __restrict__ d_s) {
+    extern __shared__ float4 s_row4[];
+    float* sw = reinterpret_cast<float*>(s_row4);
+    __shared__ float s_part[32];
+    __shared__ float s_dot;
+    const int co = blockIdx.x;
+    const int n = Cin * kk;
+    stage_row(w + (size_t)co * n, sw, n >> 2);
+    __syncthreads();
+    const float d = demodulate ? demod[co] : 1.f;
+    float dot = 0.f;
+    if (demodulate) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int t = i / Cin, ci = i - t * Cin;
+            const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
+            dot += to_f(d_wout[o]) * (scale * sw[ci * kk + t] * s[ci]);
+        }
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = dot;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.f;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (threadIdx.x == 0) s_dot = v;
+        }
+        __syncthreads();   // also orders the dot-phase reads of sw before the in-place overwrite below
+        dot = s_dot;
+    }
+    const float d3dot = demodulate ? d * d * d * dot : 0.f;
+    for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+        float ds = 0.f;
+        const float sc = s[ci];
+        for (int t = 0; t < kk; ++t) {
+            const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
+            const float wv = sw[ci * kk + t];
+            const float u = scale * wv * sc;
+            const float du = d * to_f(d_wout[o]) - u * d3dot;
+            sw[ci * kk + t] = du * scale * sc;   // element owned by this thread only
+            ds += du * scale * wv;
+        }
+        atomicAdd(&d_s[ci], ds);
+    }
+    __syncthreads();
+    float4* out4 = reinterpret_cast<float4*>(d_w + (size_t)co * n);
+    for (int j = threadIdx.x; j < (n >> 2); j += blockDim.x) out4[j] = s_row4[j];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) sum_batch_kernel(const T* __restrict__ x, T* __restrict__ y, int V, int64_t nvec) {
     constexpr int VN = VecOf<T>::N;
@@ -344,7 +514,7 @@ __global__ void __launch_bounds__(256) sum_batch_kernel(const T* __restrict__ x,
         for (int k = 0; k < VN; ++k) acc[k] = 0.f;
         for (int v = 0; v < V; ++v) {
             float f[VN];
-            unpack(reinterpret_cast<const Vt*>(x)[(int64_t)v * nvec + i], f);
+            unpack(ld_vec<Vt>(reinterpret_cast<const Vt*>(x) + (int64_t)v * nvec + i), f);
 #pragma unroll
             for (int k = 0; k < VN; ++k) acc[k] += f[k];
         }
@@ -428,6 +598,11 @@ __global__ void __launch_bounds__(256) bilinear2x_bwd_kernel(const T* __restrict
 
 inline int grid_for(int64_t total, int block = 256) { return (int)((total + block - 1) / block); }
 
+// modweight_*_smem_kernel preconditions: float4-able rows that fit the default 48 KB of dynamic shared memory
+inline bool row_fits_smem(int64_t n, const void* a, const void* b) {
+    return n % 4 == 0 && n * 4 <= 48 * 1024 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0;
+}
+
 }  // namespace agr
 
 using namespace agr;
@@ -448,7 +623,13 @@ int agr_upfirdn2d(int32_t dtype, const void* x, void* y, int32_t N, int32_t H, i
         (const T*)x, (T*)y, N, H, W, C, out_h, out_w, fp)
 #define AGR_FIR_SHAPE(T, VEC, VN)                                                                                       \
     do {                                                                                                                \
-        if (kh == 4 && kw == 4 && up == 1 && down == 1) AGR_FIR_LAUNCH(T, VEC, VN, 1, 1, 4);                            \
+        if (kh == 4 && kw == 4 && up == 1 && down == 1) {                                                               \
+            /* strips once the strip grid still fills the machine; the per-pixel kernel keeps tiny maps parallel */    \
+            const int64_t strip_threads = (int64_t)N * ((out_h + 3) / 4) * out_w * (C / VN);                            \
+            if (VEC && strip_threads >= 148 * 1024)                                                                     \
+                blur_strip_kernel<T, 4, 4><<<grid_for(strip_threads), 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C, out_h, out_w, fp); \
+            else AGR_FIR_LAUNCH(T, VEC, VN, 1, 1, 4);                                                                   \
+        }                                                                                                               \
         else if (kh == 4 && kw == 4 && up == 2 && down == 1) AGR_FIR_LAUNCH(T, VEC, VN, 2, 1, 4);                       \
         else if (kh == 4 && kw == 4 && up == 1 && down == 2) AGR_FIR_LAUNCH(T, VEC, VN, 1, 2, 4);                       \
         else AGR_FIR_LAUNCH(T, VEC, VN, 0, 0, 0);                                                                       \
@@ -520,7 +701,11 @@ int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx
     const int cv = vec ? C / VN : C;
     if (cv > 256) return AGR_ERR_INVALID_ARGUMENT;  // up to 2048 bf16 / 1024 fp32 channels
     const int lanes = 256 / cv;
-    int ppb = lanes * 16;  // pixels per block
+    // serial pixels per lane: 16 on large maps (amortises the C atomics a block ends with), fewer when that would
+    // leave most SMs idle -- the small maps of the coarse levels were latency-bound at 16 dependent iterations
+    int64_t iters = pixels / ((int64_t)lanes * 148 * 2);
+    iters = iters < 1 ? 1 : (iters > 16 ? 16 : iters);
+    int ppb = lanes * (int)iters;  // pixels per block
     int64_t blocks = (pixels + ppb - 1) / ppb;
     if (blocks > 148 * 16) { blocks = 148 * 16; ppb = (int)((pixels + blocks - 1) / blocks); }
     const size_t smem = (size_t)(C + 1) * sizeof(float);
@@ -571,7 +756,12 @@ int agr_modweight_forward(int32_t dtype, const float* w, const float* s, float s
                           int32_t demodulate, int32_t transpose_io, void* w_out, float* demod_out, void* cuda_stream) {
     if (!w || !s || !w_out || Cout < 1 || Cin < 1 || k < 1) return AGR_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    if (dtype == AGR_BF16) modweight_fwd_kernel<__nv_bfloat16><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (__nv_bfloat16*)w_out, demod_out);
+    const int64_t n = (int64_t)Cin * k * k;
+    if (row_fits_smem(n, w, w)) {
+        const size_t smem = (size_t)n * sizeof(float);
+        if (dtype == AGR_BF16) modweight_fwd_smem_kernel<__nv_bfloat16><<<Cout, 256, smem, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (__nv_bfloat16*)w_out, demod_out);
+        else modweight_fwd_smem_kernel<float><<<Cout, 256, smem, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (float*)w_out, demod_out);
+    } else if (dtype == AGR_BF16) modweight_fwd_kernel<__nv_bfloat16><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (__nv_bfloat16*)w_out, demod_out);
     else modweight_fwd_kernel<float><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (float*)w_out, demod_out);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
@@ -581,7 +771,12 @@ int agr_modweight_backward(int32_t dtype, const float* w, const float* s, float 
                            float* d_s, void* cuda_stream) {
     if (!w || !s || !d_wout || !d_w || !d_s || (demodulate && !demod)) return AGR_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    if (dtype == AGR_BF16) modweight_bwd_kernel<__nv_bfloat16><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const __nv_bfloat16*)d_wout, demod, d_w, d_s);
+    const int64_t n = (int64_t)Cin * k * k;
+    if (row_fits_smem(n, w, d_w)) {
+        const size_t smem = (size_t)n * sizeof(float);
+        if (dtype == AGR_BF16) modweight_bwd_smem_kernel<__nv_bfloat16><<<Cout, 256, smem, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const __nv_bfloat16*)d_wout, demod, d_w, d_s);
+        else modweight_bwd_smem_kernel<float><<<Cout, 256, smem, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const float*)d_wout, demod, d_w, d_s);
+    } else if (dtype == AGR_BF16) modweight_bwd_kernel<__nv_bfloat16><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const __nv_bfloat16*)d_wout, demod, d_w, d_s);
     else modweight_bwd_kernel<float><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const float*)d_wout, demod, d_w, d_s);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }

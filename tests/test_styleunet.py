@@ -117,7 +117,8 @@ def _cmp(a, b, tol):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("C,H,W,kind", [(64, 32, 48, "blur1"), (3, 33, 17, "down"), (12, 16, 16, "up"), (128, 9, 9, "blur2"),
-                                         (32, 20, 12, "up"), (8, 15, 15, "blur1")])
+                                         (32, 20, 12, "up"), (8, 15, 15, "blur1"),
+                                         (16, 517, 600, "blur1"), (64, 300, 300, "blur2")])   # last two: blur_strip_kernel, ragged last strip
 def test_upfirdn2d_matches_oracle(C, H, W, kind, dtype, tol, built_lib):
     from animatablegaussians_b200 import styleunet_ops as ops
     from oracle import styleunet_oracle as so
@@ -188,7 +189,8 @@ def test_bias_act_matches_oracle(C, H, activate, noise, dtype, tol, built_lib):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
-@pytest.mark.parametrize("Cout,Cin,k,demod,tr", [(64, 32, 3, True, False), (12, 64, 1, False, False), (32, 48, 3, True, True), (128, 128, 3, False, False)])
+@pytest.mark.parametrize("Cout,Cin,k,demod,tr", [(64, 32, 3, True, False), (12, 64, 1, False, False), (32, 48, 3, True, True), (128, 128, 3, False, False),
+                                                 (16, 1024, 3, True, False), (16, 3, 3, True, False), (8, 2048, 3, True, True)])  # smem row / unaligned row / row > 48 KB
 def test_modweight_matches_oracle(Cout, Cin, k, demod, tr, dtype, tol, built_lib):
     from animatablegaussians_b200 import styleunet_ops as ops
     from oracle import styleunet_oracle as so
