@@ -504,6 +504,49 @@ __global__ void __launch_bounds__(256) modweight_bwd_smem_kernel(const float* __
     for (int j = threadIdx.x; j < (n >> 2); j += blockDim.x) out4[j] = s_row4[j];
 }
 
+// ------------------------------------------------------------------------------------------------ EqualLinear (style vector)
+// forward: one warp per output row.
+__global__ void __launch_bounds__(256) equal_linear_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                              const float* __restrict__ x, float scale, float lr_mul, int out_dim,
+                                                              int in_dim, float* __restrict__ y) {
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= out_dim) return;
+    const float* wr = w + (size_t)row * in_dim;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = lane; i < in_dim; i += 32) acc += wr[i] * x[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[row] = (bias ? lr_mul * bias[row] : 0.f) + scale * acc;
+}
+
+// backward: a block owns ROWS output rows and walks the columns; d_w rows are written coalesced, the column sums of
+// the block's rows go to d_x with one atomic per (block, column).
+template <int ROWS>
+__global__ void __launch_bounds__(256) equal_linear_bwd_kernel(const float* __restrict__ w, const float* __restrict__ x,
+                                                              const float* __restrict__ dy, float scale, float lr_mul, int out_dim,
+                                                              int in_dim, float* __restrict__ d_w, float* __restrict__ d_bias,
+                                                              float* __restrict__ d_x) {
+    const int j0 = blockIdx.x * ROWS;
+    float g[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) g[r] = (j0 + r < out_dim) ? dy[j0 + r] : 0.f;
+    if (d_bias && threadIdx.x < ROWS && j0 + threadIdx.x < out_dim) d_bias[j0 + threadIdx.x] = lr_mul * dy[j0 + threadIdx.x];
+    for (int i = threadIdx.x; i < in_dim; i += blockDim.x) {
+        const float xi = x[i];
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            if (j0 + r < out_dim) {
+                const size_t o = (size_t)(j0 + r) * in_dim + i;
+                acc += w[o] * g[r];
+                d_w[o] = scale * g[r] * xi;
+            }
+        }
+        if (d_x) atomicAdd(&d_x[i], scale * acc);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) sum_batch_kernel(const T* __restrict__ x, T* __restrict__ y, int V, int64_t nvec) {
     constexpr int VN = VecOf<T>::N;
@@ -749,6 +792,23 @@ int agr_sum_batch(int32_t dtype, const void* x, void* y, int32_t V, int64_t n, v
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     if (dtype == AGR_BF16) sum_batch_kernel<__nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, V, nvec);
     else sum_batch_kernel<float><<<g, 256, 0, s>>>((const float*)x, (float*)y, V, nvec);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_equal_linear_forward(const float* w, const float* bias, const float* x, float scale, float lr_mul, int32_t out_dim,
+                             int32_t in_dim, float* y, void* cuda_stream) {
+    if (!w || !x || !y || out_dim < 1 || in_dim < 1) return AGR_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    equal_linear_fwd_kernel<<<grid_for((int64_t)out_dim * 32), 256, 0, st>>>(w, bias, x, scale, lr_mul, out_dim, in_dim, y);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_equal_linear_backward(const float* w, const float* x, const float* dy, float scale, float lr_mul, int32_t out_dim,
+                              int32_t in_dim, float* d_w, float* d_bias, float* d_x, void* cuda_stream) {
+    if (!w || !x || !dy || !d_w || out_dim < 1 || in_dim < 1) return AGR_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    constexpr int ROWS = 4;
+    equal_linear_bwd_kernel<ROWS><<<(out_dim + ROWS - 1) / ROWS, 256, 0, st>>>(w, x, dy, scale, lr_mul, out_dim, in_dim, d_w, d_bias, d_x);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 

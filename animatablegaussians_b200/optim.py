@@ -1,7 +1,12 @@
 """Flat-bucket Adam: all trainable parameters of the avatar live in ONE fp32 buffer (and their gradients in
 another), so that (a) the view-sharded step needs exactly one NCCL all-reduce and (b) the optimizer is one
 fused streaming kernel (include/agr_optim.h).  Mirrors torch.optim.Adam(lr) + step() + zero_grad() of the
-reference trainer (main_avatar.py:49-51,255-256)."""
+reference trainer (main_avatar.py:49-51,255-256).
+
+Gradients reach the bucket lazily: after `step()` / `zero_grad()` every `p.grad` is None (torch's set_to_none default),
+so autograd hands each parameter its freshly produced gradient tensor without launching an accumulation kernel
+(r01 profile: ~800 `p.grad += g` launches per step otherwise); `flat_grad` / `all_reduce()` / `step()` first gather
+those tensors into the bucket with one multi-tensor copy and re-point `p.grad` at the bucket views."""
 import ctypes as C
 
 import torch
@@ -29,16 +34,46 @@ class FlatAdam:
             total += (p.numel() + 3) // 4 * 4
         self.numel = n
         self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._grad_views = []
         for p, o in zip(self.params, offs):
             k = p.numel()
             self.flat_param[o:o + k].copy_(p.data.reshape(-1))
             p.data = self.flat_param[o:o + k].view_as(p.data)
-            p.grad = self.flat_grad[o:o + k].view_as(p.data)
+            self._grad_views.append(self._flat_grad[o:o + k].view_as(p.data))
+            p.grad = None
+        self._bucket_clean = True   # bucket is all-zero: gathered gradients can be copied instead of added
         self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
         self.device_step = torch.zeros(1, dtype=torch.int32, device=dev)  # used by step(graph_safe=True)
+
+    def gather_grads(self):
+        """Move the gradients autograd left in `p.grad` into the bucket (multi-tensor copy when the bucket is known to
+        be zero, multi-tensor add otherwise) and re-point `p.grad` at the bucket views.  Idempotent."""
+        views, grads = [], []
+        for p, v in zip(self.params, self._grad_views):
+            g = p.grad
+            if g is None or g.data_ptr() == v.data_ptr():
+                continue
+            views.append(v)
+            grads.append(g.detach().to(torch.float32).view_as(v) if g.dtype != torch.float32 or g.shape != v.shape else g.detach())
+        if views:
+            with torch.no_grad():
+                if self._bucket_clean:
+                    torch._foreach_copy_(views, grads)
+                else:
+                    torch._foreach_add_(views, grads)
+            self._bucket_clean = False
+        for p, v in zip(self.params, self._grad_views):
+            if p.grad is not None:
+                p.grad = v
+
+    @property
+    def flat_grad(self):
+        """The gradient bucket, with every pending `p.grad` gathered."""
+        self.gather_grads()
+        return self._flat_grad
 
     def all_reduce(self, group=None):
         """The ONE collective of the view-sharded step: sum of the flat gradient bucket."""
@@ -49,24 +84,36 @@ class FlatAdam:
         """graph_safe=True keeps the step counter on the device so the call can be captured in a CUDA graph."""
         lib = _lib.load()
         dev = self.flat_param.device
+        self.gather_grads()
         if graph_safe:
             with torch.cuda.device(dev), stats.stage("adam", launches=2):
                 st = lib.agr_adam_step_graph(self.flat_param.numel(), C.c_void_p(self.flat_param.data_ptr()),
-                                             C.c_void_p(self.flat_grad.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
+                                             C.c_void_p(self._flat_grad.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
                                              C.c_void_p(self.exp_avg_sq.data_ptr()), self.lr, self.betas[0], self.betas[1],
                                              self.eps, C.c_void_p(self.device_step.data_ptr()), grad_scale, int(zero_grad),
                                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
             if st != _lib.AGR_OK:
                 raise RuntimeError("agr_adam_step_graph failed: %d" % st)
+            self._after_step(zero_grad)
             return
         self.t += 1
         with torch.cuda.device(dev), stats.stage("adam", launches=1):
             st = lib.agr_adam_step(self.flat_param.numel(), C.c_void_p(self.flat_param.data_ptr()),
-                                   C.c_void_p(self.flat_grad.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
+                                   C.c_void_p(self._flat_grad.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
                                    C.c_void_p(self.exp_avg_sq.data_ptr()), self.lr, self.betas[0], self.betas[1], self.eps,
                                    self.t, grad_scale, int(zero_grad), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         if st != _lib.AGR_OK:
             raise RuntimeError("agr_adam_step failed: %d" % st)
+        self._after_step(zero_grad)
+
+    def _after_step(self, zero_grad):
+        if zero_grad:   # the kernel cleared the bucket; next backward hands over fresh tensors (set_to_none semantics)
+            self._bucket_clean = True
+            for p in self.params:
+                p.grad = None
 
     def zero_grad(self):
-        self.flat_grad.zero_()
+        self._flat_grad.zero_()
+        self._bucket_clean = True
+        for p in self.params:
+            p.grad = None

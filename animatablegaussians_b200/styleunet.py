@@ -105,10 +105,10 @@ class EqualLinear(nn.Module):
         self.lr_mul = lr_mul
 
     def forward(self, x):
-        b = self.bias * self.lr_mul if self.bias is not None else None
         if self.activation:
+            b = self.bias * self.lr_mul if self.bias is not None else None
             return ops.bias_act(nn.functional.linear(x, self.weight * self.scale), b)
-        return nn.functional.linear(x, self.weight * self.scale, bias=b)
+        return ops.equal_linear(x, self.weight, self.bias, self.scale, self.lr_mul)
 
 
 class EqualConv2d(nn.Module):

@@ -42,6 +42,8 @@ _lib.register_symbols({
     "agr_bilinear2x_add_forward": (C.c_int, [C.c_int32, _p, _p, _p] + [C.c_int32] * 5 + [_p]),
     "agr_bilinear2x_backward": (C.c_int, [C.c_int32, _p, _p] + [C.c_int32] * 4 + [_p]),
     "agr_conv2d_tc_forward_split": (C.c_int, [_p, _p, _p] + [C.c_int32] * 9 + [_p, _p, C.c_int32, _p]),
+    "agr_equal_linear_forward": (C.c_int, [_p, _p, _p, C.c_float, C.c_float, C.c_int32, C.c_int32, _p, _p]),
+    "agr_equal_linear_backward": (C.c_int, [_p, _p, _p, C.c_float, C.c_float, C.c_int32, C.c_int32, _p, _p, _p, _p]),
 })
 
 _COMPUTE_DTYPE = torch.float32
@@ -106,7 +108,38 @@ def _new_like(x, C_, H, W):
 
 
 # ------------------------------------------------------------------------------------------ FIR resampling
+import contextlib  # noqa: E402
 import weakref  # noqa: E402
+
+# ------------------------------------------------------------------------------------------ zero-initialised scratch
+# The reduction targets of the backward kernels (bias / noise-weight / style gradients, accumulated with atomics) must
+# start at zero.  One torch.zeros per target is ~530 fill launches per train step (r01 profile); inside `step_arena()`
+# they are carved from chunks that are zero-filled once.  A chunk is never handed out twice and dies with its last
+# slice, so nothing carries over between steps or across CUDA-graph capture boundaries.
+_arena = None
+
+
+@contextlib.contextmanager
+def step_arena(chunk_floats=1 << 18):
+    """Wrap ONE forward+backward (eager, or the body of a CUDA-graph capture)."""
+    global _arena
+    prev, _arena = _arena, {"buf": None, "off": 0, "chunk": int(chunk_floats)}
+    try:
+        yield
+    finally:
+        _arena = prev
+
+
+def _zeros(n, dev):
+    a = _arena
+    if a is None or n > a["chunk"]:
+        return torch.zeros(n, dtype=torch.float32, device=dev)
+    if a["buf"] is None or a["buf"].device != dev or a["off"] + n > a["chunk"]:
+        a["buf"], a["off"] = torch.zeros(a["chunk"], dtype=torch.float32, device=dev), 0
+    out = a["buf"][a["off"]:a["off"] + n]
+    a["off"] += (n + 3) // 4 * 4   # keep every slice 16-byte aligned
+    return out
+
 
 _taps_cache = {}
 
@@ -264,8 +297,8 @@ class _BiasAct(torch.autograd.Function):
         activate, is4, has_b, has_n, Cc, pixels, bshape, nshape = ctx.meta
         g = _nhwc(g) if is4 else g.contiguous()
         dx = torch.empty_like(g)
-        db = torch.zeros(Cc, dtype=torch.float32, device=g.device) if has_b else None
-        dn = torch.zeros(1, dtype=torch.float32, device=g.device) if has_n else None
+        db = _zeros(Cc, g.device) if has_b else None
+        dn = _zeros(1, g.device) if has_n else None
         with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
             _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dx), pixels, Cc, _ptr(nz) if has_n else None,
                                              nz.numel() if has_n else 1, _ptr(db), _ptr(dn), int(activate), _stream(g)),
@@ -355,11 +388,52 @@ class _ModWeight(torch.autograd.Function):
         scale, Cout, Cin, k, demodulate, transpose_io, wshape, sshape = ctx.meta
         g = g.contiguous(memory_format=_CL)
         dw = torch.empty_like(w)
-        ds = torch.zeros(Cin, dtype=torch.float32, device=w.device)
+        ds = _zeros(Cin, w.device)
         with torch.cuda.device(w.device), stats.stage("styleunet_weight", launches=1):
             _check(lib.agr_modweight_backward(_code(g), _ptr(w), _ptr(sv), scale, Cout, Cin, k, int(demodulate), int(transpose_io),
                                               _ptr(g), _ptr(demod), _ptr(dw), _ptr(ds), _stream(w)), "agr_modweight_backward")
         return dw.view(wshape), ds.view(sshape), None, None, None, None
+
+
+class _EqualLinearVec(torch.autograd.Function):
+    """EqualLinear (no activation) on one style vector: lr_mul * bias + scale * W x, one launch each way."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, scale, lr_mul):
+        lib = _lib.load()
+        out_dim, in_dim = weight.shape
+        xv, w = x.detach().contiguous().view(-1), weight.detach().contiguous()
+        b = bias.detach().contiguous() if bias is not None else None
+        y = torch.empty(out_dim, dtype=torch.float32, device=w.device)
+        with torch.cuda.device(w.device), stats.stage("styleunet_weight", launches=1):
+            _check(lib.agr_equal_linear_forward(_ptr(w), _ptr(b), _ptr(xv), float(scale), float(lr_mul), out_dim, in_dim, _ptr(y),
+                                                _stream(w)), "agr_equal_linear_forward")
+        ctx.save_for_backward(xv, w)
+        ctx.meta = (float(scale), float(lr_mul), bias is not None, x.shape)
+        return y.view(1, out_dim)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        xv, w = ctx.saved_tensors
+        scale, lr_mul, has_b, xshape = ctx.meta
+        out_dim, in_dim = w.shape
+        g = g.contiguous().view(-1)
+        dw = torch.empty_like(w)
+        db = torch.empty(out_dim, dtype=torch.float32, device=w.device) if has_b else None
+        dx = _zeros(in_dim, w.device) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(w.device), stats.stage("styleunet_weight", launches=1):
+            _check(lib.agr_equal_linear_backward(_ptr(w), _ptr(xv), _ptr(g), scale, lr_mul, out_dim, in_dim, _ptr(dw), _ptr(db),
+                                                 _ptr(dx), _stream(w)), "agr_equal_linear_backward")
+        return (dx.view(xshape) if dx is not None else None), dw, db, None, None
+
+
+def equal_linear(x, weight, bias, scale, lr_mul):
+    """dual_styleunet.py:155-158.  The fused kernels cover the case the U-Nets run 108 times per step (one fp32 style
+    vector); a batch of styles is a plain library GEMM."""
+    if x.is_cuda and x.dim() == 2 and x.shape[0] == 1 and x.dtype == torch.float32 and weight.dtype == torch.float32:
+        return _EqualLinearVec.apply(x, weight, bias, scale, lr_mul)
+    return F.linear(x, weight * scale, bias=bias * lr_mul if bias is not None else None)
 
 
 _ones_cache = {}
@@ -418,8 +492,8 @@ class _ConvAct(torch.autograd.Function):
         pixels = g.shape[0] * g.shape[2] * g.shape[3]
         if activate or has_b or has_n:
             dz = torch.empty_like(g)
-            db = torch.zeros(Cout, dtype=torch.float32, device=g.device) if has_b else None
-            dn = torch.zeros(1, dtype=torch.float32, device=g.device) if has_n else None
+            db = _zeros(Cout, g.device) if has_b else None
+            dn = _zeros(1, g.device) if has_n else None
             with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
                 _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dz), pixels, Cout, _ptr(nz) if has_n else None,
                                                  nz.numel() if has_n else 1, _ptr(db), _ptr(dn), int(activate), _stream(g)),
@@ -479,7 +553,7 @@ class _SplitConvAct(torch.autograd.Function):
         g = _nhwc(g)
         pixels = g.shape[0] * g.shape[2] * g.shape[3]
         dz = torch.empty_like(g)
-        db = torch.zeros(Cout, dtype=torch.float32, device=g.device) if has_b else None
+        db = _zeros(Cout, g.device) if has_b else None
         with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
             _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dz), pixels, Cout, None, 1, _ptr(db), None,
                                              int(activate), _stream(g)), "agr_bias_act_backward")

@@ -115,6 +115,11 @@ class ProductWorkload:
         self.graph = None
 
     def _body(self):
+        from animatablegaussians_b200 import styleunet_ops as ops
+        with ops.step_arena():
+            return self._body_impl()
+
+    def _body_impl(self):
         items = {"smpl_pos_map": self.d_pose, "cano2live_jnt_mats": self.d_mats}
         out = self.net.render_views(items, return_depth=True, views=self.views_dev)
         # plain sums so that colour, depth AND alpha receive gradients + offset regulariser

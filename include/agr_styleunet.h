@@ -100,6 +100,18 @@ int agr_bilinear2x_backward(int32_t dtype, const void* g, float* d_vf, int32_t V
  * V views of a batch (ATen's strided reduction reaches ~0.3 TB/s on this shape; this streams at HBM rate). */
 int agr_sum_batch(int32_t dtype, const void* x, void* y, int32_t V, int64_t n, void* cuda_stream);
 
+/* EqualLinear on ONE style vector -- the modulation layer of every ModulatedConv2d (dual_styleunet.py:150-160, no
+ * activation; called at dual_styleunet.py:244 with a (1, style_dim) input).  fp32:
+ *   y[j] = lr_mul * bias[j] + scale * sum_i w[j][i] * x[i]                       w (out_dim, in_dim) row-major
+ * backward: d_w[j][i] = scale * dy[j] * x[i];  d_bias[j] = lr_mul * dy[j];  d_x[i] += scale * sum_j w[j][i] * dy[j].
+ * d_x must be zero-initialised by the caller (accumulated with atomics); d_bias / d_x / bias may be NULL.
+ * One launch each instead of the reference's mul, mul, addmm (forward) and mm, mm, mul, mul, sum (autograd backward):
+ * the three U-Nets hold 108 of these layers, ~900 tiny launches per step. */
+int agr_equal_linear_forward(const float* w, const float* bias, const float* x, float scale, float lr_mul, int32_t out_dim,
+                             int32_t in_dim, float* y, void* cuda_stream);
+int agr_equal_linear_backward(const float* w, const float* x, const float* dy, float scale, float lr_mul, int32_t out_dim,
+                              int32_t in_dim, float* d_w, float* d_bias, float* d_x, void* cuda_stream);
+
 /* w_out[ci][k*k-1-t][co] = w_krsc[co][t][ci]  (bf16) */
 int agr_weight_flip_transpose(const void* w_krsc, void* w_out, int32_t Cout, int32_t Cin, int32_t ksize, void* cuda_stream);
 

@@ -25,7 +25,11 @@ def _worker(rank, world, port, ret):
     xs = torch.randn(n_views, 4, 7, generator=g)      # one "view" = one mini-batch
     loss = sum(net(xs[v]).pow(2).sum() for v in views)
     loss.backward()
-    assert all(p.grad.data_ptr() >= opt.flat_grad.data_ptr() for p in net.parameters())  # grads live in the bucket
+    fresh = [p.grad for p in net.parameters()]
+    bucket = opt.flat_grad                               # gathers autograd's tensors into the bucket ...
+    lo, hi = bucket.data_ptr(), bucket.data_ptr() + bucket.numel() * 4
+    assert all(lo <= p.grad.data_ptr() < hi for p in net.parameters())   # ... and re-points p.grad at it
+    assert all(torch.equal(f, p.grad) for f, p in zip(fresh, net.parameters()))
     opt.all_reduce()
     ret[rank] = (views, opt.flat_grad.clone(), opt.flat_param.clone())
     dist.destroy_process_group()
@@ -50,3 +54,39 @@ def test_view_shard_and_single_allreduce():
     xs = torch.randn(16, 4, 7, generator=g)
     sum(net(xs[v]).pow(2).sum() for v in range(16)).backward()
     assert torch.allclose(opt.flat_grad, g0, rtol=1e-5, atol=1e-6)
+
+
+def test_lazy_gradient_gather_semantics():
+    """FlatAdam: p.grad is None after zero_grad (autograd then hands over its tensor: no accumulate launch); the bucket
+    equals torch's own accumulation whether backward runs once, twice before a gather, or on both sides of one."""
+    from animatablegaussians_b200 import optim
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    ref = [p.detach().clone().requires_grad_(True) for p in net.parameters()]
+    opt = optim.FlatAdam(net.parameters(), lr=1e-3)
+    assert all(p.grad is None for p in net.parameters())
+    x1, x2, x3 = torch.randn(4, 6), torch.randn(4, 6), torch.randn(4, 6)
+
+    def f(ps, x):
+        return (torch.tanh(x @ ps[0].t() + ps[1]) @ ps[2].t() + ps[3]).pow(2).sum()
+
+    ps = list(net.parameters())
+    f(ps, x1).backward(); f(ps, x2).backward()          # two backwards before the first gather
+    g12 = opt.flat_grad.clone()
+    f(ps, x3).backward()                                 # accumulates into the bucket views in place
+    g123 = opt.flat_grad.clone()
+    (f(ref, x1) + f(ref, x2)).backward()
+    want12 = torch.cat([r.grad.reshape(-1) for r in ref])
+    f(ref, x3).backward()
+    want123 = torch.cat([r.grad.reshape(-1) for r in ref])
+    def flat(bucket):   # the bucket pads every tensor to 4 elements: pick the parameters' own ranges
+        return torch.cat([bucket[v.storage_offset():v.storage_offset() + v.numel()] for v in opt._grad_views])
+
+    assert torch.allclose(flat(g12), want12, rtol=1e-6, atol=1e-7) and torch.allclose(flat(g123), want123, rtol=1e-6, atol=1e-7)
+    opt.zero_grad()
+    assert all(p.grad is None for p in ps) and float(opt.flat_grad.abs().max()) == 0.0
+    f(ps, x2).backward()
+    for r in ref:
+        r.grad = None
+    f(ref, x2).backward()
+    assert torch.allclose(flat(opt.flat_grad), torch.cat([r.grad.reshape(-1) for r in ref]), rtol=1e-6, atol=1e-7)

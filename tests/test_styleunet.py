@@ -305,3 +305,45 @@ def test_add_view_feature_matches_interpolate(V, Vb, dtype, tol, built_lib):
     ya.backward(up); yb.backward(up.double())
     _cmp(va.grad, vb.grad, tol)
     _cmp(ba.grad, bb.grad, 2 * tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("out_dim,in_dim,bias,lr_mul", [(512, 512, True, 1.0), (64, 512, True, 1.0), (33, 70, False, 0.01), (3, 5, True, 0.5)])
+def test_equal_linear_matches_reference_expression(out_dim, in_dim, bias, lr_mul, built_lib):
+    """F.linear(x, W * scale, bias * lr_mul) (dual_styleunet.py:155-158) in float64 vs the fused style-vector kernels."""
+    from animatablegaussians_b200 import styleunet_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    W = torch.randn(out_dim, in_dim, device="cuda", generator=g)
+    b = torch.randn(out_dim, device="cuda", generator=g) if bias else None
+    x = torch.randn(1, in_dim, device="cuda", generator=g)
+    scale = lr_mul / in_dim ** 0.5
+    Wa, xa = W.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ba = b.clone().requires_grad_(True) if bias else None
+    Wb, xb = W.double().requires_grad_(True), x.double().requires_grad_(True)
+    bb = b.double().requires_grad_(True) if bias else None
+    with ops.step_arena():
+        ya = ops.equal_linear(xa, Wa, ba, scale, lr_mul)
+        yb = torch.nn.functional.linear(xb, Wb * scale, bias=bb * lr_mul if bias else None)
+        _cmp(ya, yb, 1e-5)
+        up = torch.randn(1, out_dim, device="cuda", generator=g)
+        ya.backward(up); yb.backward(up.double())
+    _cmp(Wa.grad, Wb.grad, 1e-5)
+    _cmp(xa.grad, xb.grad, 1e-5)
+    if bias:
+        _cmp(ba.grad, bb.grad, 1e-6)
+
+
+@pytest.mark.gpu
+def test_step_arena_hands_out_disjoint_zeroed_slices(built_lib):
+    from animatablegaussians_b200 import styleunet_ops as ops
+    dev = torch.device("cuda:0")
+    with ops.step_arena(chunk_floats=64):
+        a, b = ops._zeros(5, dev), ops._zeros(7, dev)
+        a.fill_(1.0); b.fill_(2.0)
+        c = ops._zeros(60, dev)          # does not fit the open chunk: new chunk
+        d = ops._zeros(100, dev)         # larger than a chunk: plain allocation
+        assert a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and b.data_ptr() - a.data_ptr() == 32
+        assert float(c.abs().sum()) == 0 and float(d.abs().sum()) == 0 and float(a.sum()) == 5 and float(b.sum()) == 14
+    assert ops._arena is None
+    e = ops._zeros(3, dev)
+    assert float(e.abs().sum()) == 0
