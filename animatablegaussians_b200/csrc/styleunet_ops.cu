@@ -235,6 +235,93 @@ __global__ void __launch_bounds__(256) haar_kernel(const T* __restrict__ x, T* _
     }
 }
 
+// ------------------------------------------------------------------------------------------------ wavelet upsample
+// dwt(upsample_2x(iwt(skip))) of the ToRGB skip path as ONE pass.  All three stages are linear and shift-invariant up
+// to output parity, so the chain collapses (on the host, include/agr_styleunet.h) into
+//   y[2m+pi, 2n+pj, bo] = sum_{bi,di,dj} K[pi][pj][bo][bi][di][dj] * x[m+di+pi-1, n+dj+pj-1, bi]        (zero outside)
+// per colour channel.  A thread owns one skip pixel x one colour channel: 36 loads -> 2x2 output pixels x 4 bands.
+// The unfused chain writes and re-reads a (4h,4w,3) image with 2-byte accesses (r01 ncu: 660 us per call at V=16).
+struct WaveletTaps { float k[256]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) wavelet_up_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int h, int w, int Ci,
+                                                            WaveletTaps kp) {
+    const int64_t total = (int64_t)N * h * w * Ci;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % Ci);
+    int64_t p = idx / Ci;
+    const int n = (int)(p % w); p /= w;
+    const int m = (int)(p % h);
+    const int b = (int)(p / h);
+    const int C4 = 4 * Ci;
+    float v[3][3][4];
+#pragma unroll
+    for (int dm = 0; dm < 3; ++dm)
+#pragma unroll
+        for (int dn = 0; dn < 3; ++dn) {
+            const int yy = m + dm - 1, xx = n + dn - 1;
+            const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
+            const T* src = x + (((int64_t)b * h + yy) * w + xx) * C4 + c;
+#pragma unroll
+            for (int bi = 0; bi < 4; ++bi) v[dm][dn][bi] = in ? to_f(src[bi * Ci]) : 0.f;
+        }
+#pragma unroll
+    for (int pi = 0; pi < 2; ++pi)
+#pragma unroll
+        for (int pj = 0; pj < 2; ++pj) {
+            T* dst = y + (((int64_t)b * 2 * h + 2 * m + pi) * (2 * w) + 2 * n + pj) * C4 + c;
+#pragma unroll
+            for (int bo = 0; bo < 4; ++bo) {
+                float acc = 0.f;
+#pragma unroll
+                for (int bi = 0; bi < 4; ++bi)
+#pragma unroll
+                    for (int di = 0; di < 2; ++di)
+#pragma unroll
+                        for (int dj = 0; dj < 2; ++dj)
+                            acc += kp.k[((((pi * 2 + pj) * 4 + bo) * 4 + bi) * 2 + di) * 2 + dj] * v[di + pi][dj + pj][bi];
+                dst[bo * Ci] = from_f<T>(acc);
+            }
+        }
+}
+
+// adjoint: dx[m, n, bi] = sum_{bo,a,b} KT[bi][bo][a][b] * g[2m-1+a, 2n-1+b, bo]   (gather form, no atomics)
+template <typename T>
+__global__ void __launch_bounds__(256) wavelet_up_bwd_kernel(const T* __restrict__ g, T* __restrict__ dx, int N, int h, int w, int Ci,
+                                                            WaveletTaps kp) {
+    const int64_t total = (int64_t)N * h * w * Ci;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % Ci);
+    int64_t p = idx / Ci;
+    const int n = (int)(p % w); p /= w;
+    const int m = (int)(p % h);
+    const int b = (int)(p / h);
+    const int C4 = 4 * Ci, H2 = 2 * h, W2 = 2 * w;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = 2 * m - 1 + a;
+        if (i < 0 || i >= H2) continue;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+            const int j = 2 * n - 1 + bb;
+            if (j < 0 || j >= W2) continue;
+            const T* src = g + (((int64_t)b * H2 + i) * W2 + j) * C4 + c;
+#pragma unroll
+            for (int bo = 0; bo < 4; ++bo) {
+                const float gv = to_f(src[bo * Ci]);
+#pragma unroll
+                for (int bi = 0; bi < 4; ++bi) acc[bi] += kp.k[((bi * 4 + bo) * 4 + a) * 4 + bb] * gv;
+            }
+        }
+    }
+    T* dst = dx + (((int64_t)b * h + m) * w + n) * C4 + c;
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi) dst[bi * Ci] = from_f<T>(acc[bi]);
+}
+
 // ------------------------------------------------------------------------------------------------ bias_act
 constexpr float kSqrt2 = 1.4142135623730951f;
 
@@ -709,6 +796,24 @@ int agr_haar(int32_t dtype, int32_t mode, const void* x, void* y, int32_t N, int
     } while (0)
     if (dtype == AGR_BF16) AGR_HAAR(__nv_bfloat16, 8); else AGR_HAAR(float, 4);
 #undef AGR_HAAR
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_wavelet_upsample(int32_t dtype, int32_t adjoint, const void* x, void* y, int32_t N, int32_t h, int32_t w, int32_t Ci,
+                         const float* taps256, void* cuda_stream) {
+    if (!x || !y || !taps256 || N < 1 || h < 1 || w < 1 || Ci < 1) return AGR_ERR_INVALID_ARGUMENT;
+    WaveletTaps kp;
+    for (int i = 0; i < 256; ++i) kp.k[i] = taps256[i];
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const int g = grid_for((int64_t)N * h * w * Ci);
+    if (dtype == AGR_BF16) {
+        using T = __nv_bfloat16;
+        if (adjoint) wavelet_up_bwd_kernel<T><<<g, 256, 0, s>>>((const T*)x, (T*)y, N, h, w, Ci, kp);
+        else wavelet_up_fwd_kernel<T><<<g, 256, 0, s>>>((const T*)x, (T*)y, N, h, w, Ci, kp);
+    } else {
+        if (adjoint) wavelet_up_bwd_kernel<float><<<g, 256, 0, s>>>((const float*)x, (float*)y, N, h, w, Ci, kp);
+        else wavelet_up_fwd_kernel<float><<<g, 256, 0, s>>>((const float*)x, (float*)y, N, h, w, Ci, kp);
+    }
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 

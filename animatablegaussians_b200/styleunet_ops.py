@@ -42,6 +42,7 @@ _lib.register_symbols({
     "agr_bilinear2x_add_forward": (C.c_int, [C.c_int32, _p, _p, _p] + [C.c_int32] * 5 + [_p]),
     "agr_bilinear2x_backward": (C.c_int, [C.c_int32, _p, _p] + [C.c_int32] * 4 + [_p]),
     "agr_conv2d_tc_forward_split": (C.c_int, [_p, _p, _p] + [C.c_int32] * 9 + [_p, _p, C.c_int32, _p]),
+    "agr_wavelet_upsample": (C.c_int, [C.c_int32, C.c_int32, _p, _p] + [C.c_int32] * 4 + [C.POINTER(C.c_float), _p]),
     "agr_equal_linear_forward": (C.c_int, [_p, _p, _p, C.c_float, C.c_float, C.c_int32, C.c_int32, _p, _p]),
     "agr_equal_linear_backward": (C.c_int, [_p, _p, _p, C.c_float, C.c_float, C.c_int32, C.c_int32, _p, _p, _p, _p]),
 })
@@ -230,8 +231,106 @@ def haar_iwt(x):
     return _Haar.apply(x, False)
 
 
+def wavelet_upsample_taps(kernel):
+    """Collapse dwt(upfirdn2d(iwt(.), kernel, up=2, pad=(2,1))) into the two 256-entry filter banks of
+    agr_wavelet_upsample.  `kernel`: the (4,4) FIR as the Upsample module holds it (numpy).  The operator is assembled
+    from the definitions of its stages on a small grid in float64; an interior row / column of it is the bank.
+    Returns (forward[pi][pj][bo][bi][di][dj], adjoint[bi][bo][a][b]) as flat float64 arrays."""
+    import numpy as np
+    k = np.asarray(kernel, np.float64)
+    assert k.shape == (4, 4)
+    taps = k[::-1, ::-1]                      # upfirdn2d convolves: correlation with the flipped kernel
+    sgn = np.array([[[1, 1], [1, 1]], [[1, 1], [-1, -1]], [[1, -1], [1, -1]], [[1, -1], [-1, 1]]], np.float64)  # [band][row][col]
+    h = 6
+
+    def chain(skip):                          # (h,h,4) -> (2h,2h,4)
+        img = np.zeros((2 * h, 2 * h))
+        for p in range(2):
+            for q in range(2):                # InverseHaarTransform: pixel (p,q) of each 2x2 block
+                img[p::2, q::2] = 0.5 * sum(sgn[b, p, q] * skip[:, :, b] for b in range(4))
+        z = np.zeros((4 * h + 3, 4 * h + 3))  # zero-inserted image, pad (2, 1)
+        z[2:2 + 4 * h:2, 2:2 + 4 * h:2] = img
+        up = np.zeros((4 * h, 4 * h))
+        for ky in range(4):
+            for kx in range(4):
+                up += taps[ky, kx] * z[ky:ky + 4 * h, kx:kx + 4 * h]
+        out = np.zeros((2 * h, 2 * h, 4))
+        for b in range(4):                    # HaarTransform
+            out[:, :, b] = 0.5 * sum(sgn[b, p, q] * up[p::2, q::2] for p in range(2) for q in range(2))
+        return out
+
+    A = np.zeros((2 * h, 2 * h, 4, h, h, 4))
+    for m in range(h):
+        for n in range(h):
+            for b in range(4):
+                e = np.zeros((h, h, 4)); e[m, n, b] = 1.0
+                A[:, :, :, m, n, b] = chain(e)
+    m0 = 2
+    fwd = np.zeros((2, 2, 4, 4, 2, 2))
+    for pi in range(2):
+        for pj in range(2):
+            row = A[2 * m0 + pi, 2 * m0 + pj].copy()          # (bo, m, n, bi)
+            for di in range(2):
+                for dj in range(2):
+                    mm, nn = m0 + di + pi - 1, m0 + dj + pj - 1
+                    fwd[pi, pj, :, :, di, dj] = row[:, mm, nn, :]
+                    row[:, mm, nn, :] = 0
+            assert np.abs(row).max() < 1e-12, "wavelet upsample: support is not 2x2"
+    adj = np.zeros((4, 4, 4, 4))
+    col = A[:, :, :, m0, m0, :].copy()                         # (i, j, bo, bi)
+    for a in range(4):
+        for b in range(4):
+            adj[:, :, a, b] = col[2 * m0 - 1 + a, 2 * m0 - 1 + b].T
+            col[2 * m0 - 1 + a, 2 * m0 - 1 + b] = 0
+    assert np.abs(col).max() < 1e-12, "wavelet upsample: adjoint support is not 4x4"
+    return fwd.reshape(-1), adj.reshape(-1)
+
+
+_wavelet_cache = {}
+
+
+def _wavelet_taps(kernel):
+    """ctypes banks for a module's FIR buffer, cached like _host_taps (one D2H per buffer, none under graph capture)."""
+    key = id(kernel)
+    hit = _wavelet_cache.get(key)
+    if hit is not None and hit[0]() is kernel and hit[1] == kernel._version:
+        return hit[2]
+    f, a = wavelet_upsample_taps(kernel.detach().double().cpu().numpy())
+    out = ((C.c_float * 256)(*[float(v) for v in f]), (C.c_float * 256)(*[float(v) for v in a]))
+    if len(_wavelet_cache) > 1024:
+        _wavelet_cache.clear()
+    _wavelet_cache[key] = (weakref.ref(kernel), kernel._version, out)
+    return out
+
+
+class _WaveletUp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, skip, kernel):
+        skip = _nhwc(skip)
+        ctx.kernel = kernel
+        return _WaveletUp._run(skip, kernel, False)
+
+    @staticmethod
+    def _run(x, kernel, adjoint):
+        lib = _lib.load()
+        B, C4, H, W = x.shape
+        h, w = (H // 2, W // 2) if adjoint else (H, W)
+        y = _new_like(x, C4, h, w) if adjoint else _new_like(x, C4, 2 * h, 2 * w)
+        taps = _wavelet_taps(kernel)[1 if adjoint else 0]
+        with torch.cuda.device(x.device), stats.stage("styleunet_fir", launches=1):
+            _check(lib.agr_wavelet_upsample(_code(x), int(adjoint), _ptr(x), _ptr(y), B, h, w, C4 // 4,
+                                            C.cast(taps, C.POINTER(C.c_float)), _stream(x)), "agr_wavelet_upsample")
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return _WaveletUp._run(_nhwc(g), ctx.kernel, True), None
+
+
 def wavelet_upsample(skip, up_kernel):
-    """ToRGB skip path (dual_styleunet.py:624-631): dwt(upsample(iwt(skip)))."""
+    """ToRGB skip path (dual_styleunet.py:624-631): dwt(upsample(iwt(skip))), one fused pass for the 4-tap FIR."""
+    if tuple(up_kernel.shape) == (4, 4) and skip.shape[1] % 4 == 0:
+        return _WaveletUp.apply(skip, up_kernel)
     p = up_kernel.shape[0] - 2
     y = haar_iwt(skip)
     y = upfirdn2d(y, up_kernel, up=2, pad=((p + 1) // 2 + 1, p // 2))

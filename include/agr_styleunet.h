@@ -100,6 +100,18 @@ int agr_bilinear2x_backward(int32_t dtype, const void* g, float* d_vf, int32_t V
  * V views of a batch (ATen's strided reduction reaches ~0.3 TB/s on this shape; this streams at HBM rate). */
 int agr_sum_batch(int32_t dtype, const void* x, void* y, int32_t V, int64_t n, void* cuda_stream);
 
+/* ToRGB skip path  dwt(upsample(iwt(skip)))  (dual_styleunet.py:624-631; Upsample 30-50 = upfirdn2d(up=2, pad=(2,1)) with
+ * a 4x4 FIR, HaarTransform / InverseHaarTransform 374-425) as ONE pass over NHWC tensors with 4*Ci channels (bands
+ * ll|lh|hl|hh major, colour minor).  x (N,h,w,4Ci) -> y (N,2h,2w,4Ci).  The chain is linear, so the host collapses it
+ * into a parity-dependent 2x2-tap filter bank (`taps256`, 256 floats):
+ *   adjoint = 0:  y[2m+pi, 2n+pj, bo] = sum_{bi,di,dj} taps[pi][pj][bo][bi][di][dj] * x[m+di+pi-1, n+dj+pj-1, bi]
+ *   adjoint = 1:  x is the gradient g (N,2h,2w,4Ci), y = d_skip (N,h,w,4Ci):
+ *                 y[m, n, bi] = sum_{bo,a,b} taps[bi][bo][a][b] * g[2m-1+a, 2n-1+b, bo]
+ * (zero outside the tensor; h, w are the SKIP size in both modes).  Replaces 3 launches and a (4h,4w,Ci)
+ * intermediate each way. */
+int agr_wavelet_upsample(int32_t dtype, int32_t adjoint, const void* x, void* y, int32_t N, int32_t h, int32_t w, int32_t Ci,
+                         const float* taps256, void* cuda_stream);
+
 /* EqualLinear on ONE style vector -- the modulation layer of every ModulatedConv2d (dual_styleunet.py:150-160, no
  * activation; called at dual_styleunet.py:244 with a (1, style_dim) input).  fp32:
  *   y[j] = lr_mul * bias[j] + scale * sum_i w[j][i] * x[i]                       w (out_dim, in_dim) row-major

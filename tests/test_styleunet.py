@@ -347,3 +347,32 @@ def test_step_arena_hands_out_disjoint_zeroed_slices(built_lib):
     assert ops._arena is None
     e = ops._zeros(3, dev)
     assert float(e.abs().sum()) == 0
+
+
+def test_wavelet_upsample_banks_reproduce_the_chain():
+    """CPU: the parity-dependent filter banks agr_wavelet_upsample takes (host-derived) against the oracle's
+    dwt(upsample(iwt(.))) chain in float64 -- forward and adjoint, borders included."""
+    import numpy as np
+    from animatablegaussians_b200 import styleunet_ops as ops
+    from oracle import styleunet_oracle as so
+    k = (so.make_kernel([1, 3, 3, 1]) * 4).double()
+    f, a = ops.wavelet_upsample_taps(k.numpy())
+    f, a = f.reshape(2, 2, 4, 4, 2, 2), a.reshape(4, 4, 4, 4)
+    torch.manual_seed(0)
+    Ci, h, w = 3, 5, 7
+    x = torch.randn(1, 4 * Ci, h, w, dtype=torch.float64, requires_grad=True)
+    y = so.wavelet_upsample(x, k)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xp = np.pad(x.detach().numpy()[0].reshape(4, Ci, h, w), ((0, 0), (0, 0), (1, 1), (1, 1)))
+    gp = np.pad(g.numpy()[0].reshape(4, Ci, 2 * h, 2 * w), ((0, 0), (0, 0), (1, 2), (1, 2)))
+    out, dx = np.zeros((4, Ci, 2 * h, 2 * w)), np.zeros((4, Ci, h, w))
+    for m in range(h):
+        for n in range(w):
+            for pi in range(2):
+                for pj in range(2):
+                    win = xp[:, :, m + pi:m + pi + 2, n + pj:n + pj + 2]              # (bi, c, di, dj)
+                    out[:, :, 2 * m + pi, 2 * n + pj] = np.einsum("obij,bcij->oc", f[pi, pj], win)
+            dx[:, :, m, n] = np.einsum("ioab,ocab->ic", a, gp[:, :, 2 * m:2 * m + 4, 2 * n:2 * n + 4])
+    assert np.abs(out.reshape(1, 4 * Ci, 2 * h, 2 * w) - y.detach().numpy()).max() < 1e-12
+    assert np.abs(dx.reshape(1, 4 * Ci, h, w) - x.grad.numpy()).max() < 1e-12
