@@ -404,92 +404,14 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ modweight
-// One block per output channel. w: (Cout, Cin, k, k) fp32.
-template <typename T>
-__global__ void __launch_bounds__(256) modweight_fwd_kernel(const float* __restrict__ w, const float* __restrict__ s, float scale,
-                                                           int Cout, int Cin, int kk, int demodulate, int transpose_io,
-                                                           T* __restrict__ w_out, float* __restrict__ demod_out) {
-    __shared__ float s_part[32];
-    __shared__ float s_demod;
-    const int co = blockIdx.x;
-    const int n = Cin * kk;
-    const float* wr = w + (size_t)co * n;
-    float d = 1.f;
-    if (demodulate) {
-        float acc = 0.f;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const float u = scale * wr[i] * s[i / kk];
-            acc += u * u;
-        }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.f;
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (threadIdx.x == 0) { s_demod = rsqrtf(v + 1e-8f); if (demod_out) demod_out[co] = s_demod; }
-        }
-        __syncthreads();
-        d = s_demod;
-    }
-    // output index: KRSC [co][t][ci]  or (transpose_io) [ci][t][co]
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int t = i / Cin, ci = i - t * Cin;  // iterate with ci fastest for coalesced KRSC writes
-        const float u = scale * wr[ci * kk + t] * s[ci] * d;
-        const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
-        w_out[o] = from_f<T>(u);
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) modweight_bwd_kernel(const float* __restrict__ w, const float* __restrict__ s, float scale,
-                                                           int Cout, int Cin, int kk, int demodulate, int transpose_io,
-                                                           const T* __restrict__ d_wout, const float* __restrict__ demod,
-                                                           float* __restrict__ d_w, float* __restrict__ d_s) {
-    __shared__ float s_part[32];
-    __shared__ float s_dot;
-    const int co = blockIdx.x;
-    const int n = Cin * kk;
-    const float* wr = w + (size_t)co * n;
-    const float d = demodulate ? demod[co] : 1.f;
-    float dot = 0.f;  // sum_i dW'_i * u_i
-    if (demodulate) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int t = i / Cin, ci = i - t * Cin;
-            const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
-            dot += to_f(d_wout[o]) * (scale * wr[ci * kk + t] * s[ci]);
-        }
-        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = dot;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.f;
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (threadIdx.x == 0) s_dot = v;
-        }
-        __syncthreads();
-        dot = s_dot;
-    }
-    const float d3dot = demodulate ? d * d * d * dot : 0.f;
-    // thread owns input channels ci = threadIdx.x, +blockDim.x, ... so d_s needs one atomic per (co, ci)
-    for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
-        float ds = 0.f;
-        for (int t = 0; t < kk; ++t) {
-            const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
-            const float wv = wr[ci * kk + t];
-            const float u = scale * wv * s[ci];
-            const float du = d * to_f(d_wout[o]) - u * d3dot;   // dL/du
-            d_w[(size_t)co * n + ci * kk + t] = du * scale * s[ci];
-            ds += du * scale * wv;
-        }
-        atomicAdd(&d_s[ci], ds);
-    }
-}
-
-// Shared-memory variants (rows of <= 12288 floats, 16-byte aligned): the (Cin,k,k) master-weight row is staged with
-// coalesced float4 loads issued back to back (one DRAM round trip instead of n/256 dependent ones), the strided
-// [ci*kk+t] accesses then hit shared memory (stride kk is odd or 1: conflict-free), and the backward builds the d_w
-// row in place and writes it back coalesced.  Same per-element arithmetic and reduction order as the kernels above.
+// One block per output channel. w: (Cout, Cin, k, k) fp32.  Row bodies are shared by the per-layer kernels and the
+// grouped kernels (one launch for many layers).
+//
+// SMEM = true (rows of <= 12288 floats, 16-byte aligned): the (Cin,k,k) master-weight row is staged with coalesced
+// float4 loads issued back to back (one DRAM round trip instead of n/256 dependent ones), the strided [ci*kk+t]
+// accesses then hit shared memory (stride kk is odd or 1: conflict-free), and the backward builds the d_w row in
+// place and writes it back coalesced.  SMEM = false reads / writes global memory directly (any row).  Both variants
+// perform the same per-element arithmetic in the same order.
 __device__ __forceinline__ void stage_row(const float* __restrict__ src, float* dst, int n4) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* d4 = reinterpret_cast<float4*>(dst);
@@ -502,101 +424,150 @@ __device__ __forceinline__ void stage_row(const float* __restrict__ src, float* 
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) modweight_fwd_smem_kernel(const float* __restrict__ w, const float* __restrict__ s, float scale,
-                                                                int Cout, int Cin, int kk, int demodulate, int transpose_io,
-                                                                T* __restrict__ w_out, float* __restrict__ demod_out) {
-    extern __shared__ float4 s_row4[];
-    float* sw = reinterpret_cast<float*>(s_row4);
-    __shared__ float s_part[32];
-    __shared__ float s_demod;
-    const int co = blockIdx.x;
-    const int n = Cin * kk;
-    stage_row(w + (size_t)co * n, sw, n >> 2);
+__device__ __forceinline__ float block_sum_256(float v, float* s_part, float* s_out) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
     __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) *s_out = t;
+    }
+    __syncthreads();
+    return *s_out;
+}
+
+template <typename T, bool SMEM>
+__device__ __forceinline__ void modweight_fwd_row(const float* __restrict__ w, const float* __restrict__ s, float scale, int Cout,
+                                                  int Cin, int kk, int demodulate, int transpose_io, T* __restrict__ w_out,
+                                                  float* __restrict__ demod_out, int co, float* sw, float* s_part, float* s_val) {
+    const int n = Cin * kk;
+    const float* wr = w + (size_t)co * n;
+    if (SMEM) { stage_row(wr, sw, n >> 2); __syncthreads(); }
+    const float* row = SMEM ? sw : wr;
     float d = 1.f;
     if (demodulate) {
         float acc = 0.f;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const float u = scale * sw[i] * s[i / kk];
+            const float u = scale * row[i] * s[i / kk];
             acc += u * u;
         }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.f;
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (threadIdx.x == 0) { s_demod = rsqrtf(v + 1e-8f); if (demod_out) demod_out[co] = s_demod; }
-        }
-        __syncthreads();
-        d = s_demod;
+        const float tot = block_sum_256(acc, s_part, s_val);
+        d = rsqrtf(tot + 1e-8f);
+        if (demod_out && threadIdx.x == 0) demod_out[co] = d;
     }
+    // output index: KRSC [co][t][ci]  or (transpose_io) [ci][t][co]
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int t = i / Cin, ci = i - t * Cin;
-        const float u = scale * sw[ci * kk + t] * s[ci] * d;
+        const int t = i / Cin, ci = i - t * Cin;  // iterate with ci fastest for coalesced KRSC writes
+        const float u = scale * row[ci * kk + t] * s[ci] * d;
         const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
         w_out[o] = from_f<T>(u);
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) modweight_bwd_smem_kernel(const float* __restrict__ w, const float* __restrict__ s, float scale,
-                                                                int Cout, int Cin, int kk, int demodulate, int transpose_io,
-                                                                const T* __restrict__ d_wout, const float* __restrict__ demod,
-                                                                float* __restrict__ d_w, float* __restrict__ d_s) {
-    extern __shared__ float4 s_row4[];
-    float* sw = reinterpret_cast<float*>(s_row4);
-    __shared__ float s_part[32];
-    __shared__ float s_dot;
-    const int co = blockIdx.x;
+template <typename T, bool SMEM>
+__device__ __forceinline__ void modweight_bwd_row(const float* __restrict__ w, const float* __restrict__ s, float scale, int Cout,
+                                                  int Cin, int kk, int demodulate, int transpose_io, const T* __restrict__ d_wout,
+                                                  const float* __restrict__ demod, float* __restrict__ d_w, float* __restrict__ d_s,
+                                                  int co, float* sw, float* s_part, float* s_val) {
     const int n = Cin * kk;
-    stage_row(w + (size_t)co * n, sw, n >> 2);
-    __syncthreads();
+    const float* wr = w + (size_t)co * n;
+    if (SMEM) { stage_row(wr, sw, n >> 2); __syncthreads(); }
+    const float* row = SMEM ? sw : wr;
     const float d = demodulate ? demod[co] : 1.f;
-    float dot = 0.f;
+    float dot = 0.f;  // sum_i dW'_i * u_i
     if (demodulate) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const int t = i / Cin, ci = i - t * Cin;
             const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
-            dot += to_f(d_wout[o]) * (scale * sw[ci * kk + t] * s[ci]);
+            dot += to_f(d_wout[o]) * (scale * row[ci * kk + t] * s[ci]);
         }
-        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = dot;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.f;
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (threadIdx.x == 0) s_dot = v;
-        }
-        __syncthreads();   // also orders the dot-phase reads of sw before the in-place overwrite below
-        dot = s_dot;
+        dot = block_sum_256(dot, s_part, s_val);   // its barriers also order the reads of sw before the overwrite below
     }
     const float d3dot = demodulate ? d * d * d * dot : 0.f;
+    float* orow = SMEM ? sw : d_w + (size_t)co * n;
+    // thread owns input channels ci = threadIdx.x, +blockDim.x, ... so d_s needs one atomic per (co, ci)
     for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
         float ds = 0.f;
         const float sc = s[ci];
         for (int t = 0; t < kk; ++t) {
             const size_t o = transpose_io ? ((size_t)ci * kk + t) * Cout + co : ((size_t)co * kk + t) * Cin + ci;
-            const float wv = sw[ci * kk + t];
+            const float wv = row[ci * kk + t];
             const float u = scale * wv * sc;
-            const float du = d * to_f(d_wout[o]) - u * d3dot;
-            sw[ci * kk + t] = du * scale * sc;   // element owned by this thread only
+            const float du = d * to_f(d_wout[o]) - u * d3dot;   // dL/du
+            orow[ci * kk + t] = du * scale * sc;                // (SMEM: element owned by this thread only)
             ds += du * scale * wv;
         }
-        atomicAdd(&d_s[ci], ds);
+        if (d_s) atomicAdd(&d_s[ci], ds);
     }
-    __syncthreads();
-    float4* out4 = reinterpret_cast<float4*>(d_w + (size_t)co * n);
-    for (int j = threadIdx.x; j < (n >> 2); j += blockDim.x) out4[j] = s_row4[j];
+    if (SMEM) {
+        __syncthreads();
+        float4* out4 = reinterpret_cast<float4*>(d_w + (size_t)co * n);
+        const float4* in4 = reinterpret_cast<const float4*>(sw);
+        for (int j = threadIdx.x; j < (n >> 2); j += blockDim.x) out4[j] = in4[j];
+    }
+}
+
+template <typename T, bool SMEM>
+__global__ void __launch_bounds__(256) modweight_fwd_kernel(const float* __restrict__ w, const float* __restrict__ s, float scale,
+                                                           int Cout, int Cin, int kk, int demodulate, int transpose_io,
+                                                           T* __restrict__ w_out, float* __restrict__ demod_out) {
+    extern __shared__ float4 s_row4[];
+    __shared__ float s_part[32];
+    __shared__ float s_val;
+    modweight_fwd_row<T, SMEM>(w, s, scale, Cout, Cin, kk, demodulate, transpose_io, w_out, demod_out, blockIdx.x,
+                               reinterpret_cast<float*>(s_row4), s_part, &s_val);
+}
+
+template <typename T, bool SMEM>
+__global__ void __launch_bounds__(256) modweight_bwd_kernel(const float* __restrict__ w, const float* __restrict__ s, float scale,
+                                                           int Cout, int Cin, int kk, int demodulate, int transpose_io,
+                                                           const T* __restrict__ d_wout, const float* __restrict__ demod,
+                                                           float* __restrict__ d_w, float* __restrict__ d_s) {
+    extern __shared__ float4 s_row4[];
+    __shared__ float s_part[32];
+    __shared__ float s_val;
+    modweight_bwd_row<T, SMEM>(w, s, scale, Cout, Cin, kk, demodulate, transpose_io, d_wout, demod, d_w, d_s, blockIdx.x,
+                               reinterpret_cast<float*>(s_row4), s_part, &s_val);
+}
+
+// Grouped form: every conv layer of a U-Net in a few launches (the per-layer kernels are latency-bound: 58 layers x 3
+// nets x (fwd + bwd) = 348 launches of 3-15 us moving ~4 GB in total).  Layer descriptors travel as kernel parameters;
+// a block finds its layer by scanning the block-offset table.
+constexpr int kModGroup = 40;
+struct ModEntry {
+    const float* w; const float* s; const float* demod_in; float* demod_out;
+    const void* d_wout; void* w_out; float* d_w; float* d_s;
+    float scale; int Cout, Cin, kk, flags, block_begin;   // flags: 1 demodulate, 2 transpose_io, 4 row fits shared memory
+};
+struct ModGroup { ModEntry e[kModGroup]; int count; };
+
+template <typename T, bool BACKWARD>
+__global__ void __launch_bounds__(256) modweight_group_kernel(const __grid_constant__ ModGroup g) {
+    extern __shared__ float4 s_row4[];
+    __shared__ float s_part[32];
+    __shared__ float s_val;
+    int e = 0;
+    while (e + 1 < g.count && (int)blockIdx.x >= g.e[e + 1].block_begin) ++e;
+    const ModEntry& L = g.e[e];
+    const int co = blockIdx.x - L.block_begin;
+    float* sw = reinterpret_cast<float*>(s_row4);
+    const int demod = L.flags & 1, tr = (L.flags >> 1) & 1;
+    if (!BACKWARD) {
+        if (L.flags & 4) modweight_fwd_row<T, true>(L.w, L.s, L.scale, L.Cout, L.Cin, L.kk, demod, tr, static_cast<T*>(L.w_out), L.demod_out, co, sw, s_part, &s_val);
+        else modweight_fwd_row<T, false>(L.w, L.s, L.scale, L.Cout, L.Cin, L.kk, demod, tr, static_cast<T*>(L.w_out), L.demod_out, co, sw, s_part, &s_val);
+    } else {
+        if (L.flags & 4) modweight_bwd_row<T, true>(L.w, L.s, L.scale, L.Cout, L.Cin, L.kk, demod, tr, static_cast<const T*>(L.d_wout), L.demod_in, L.d_w, L.d_s, co, sw, s_part, &s_val);
+        else modweight_bwd_row<T, false>(L.w, L.s, L.scale, L.Cout, L.Cin, L.kk, demod, tr, static_cast<const T*>(L.d_wout), L.demod_in, L.d_w, L.d_s, co, sw, s_part, &s_val);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ EqualLinear (style vector)
-// forward: one warp per output row.
-__global__ void __launch_bounds__(256) equal_linear_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                                                              const float* __restrict__ x, float scale, float lr_mul, int out_dim,
-                                                              int in_dim, float* __restrict__ y) {
-    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+// forward: one warp per output row (`blk` = block index within the layer).
+__device__ __forceinline__ void equal_linear_fwd_body(const float* __restrict__ w, const float* __restrict__ bias,
+                                                      const float* __restrict__ x, float scale, float lr_mul, int out_dim,
+                                                      int in_dim, float* __restrict__ y, int blk) {
+    const int row = (blk * (int)blockDim.x + (int)threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= out_dim) return;
     const float* wr = w + (size_t)row * in_dim;
@@ -609,21 +580,21 @@ __global__ void __launch_bounds__(256) equal_linear_fwd_kernel(const float* __re
 
 // backward: a block owns ROWS output rows and walks the columns; d_w rows are written coalesced, the column sums of
 // the block's rows go to d_x with one atomic per (block, column).
-template <int ROWS>
-__global__ void __launch_bounds__(256) equal_linear_bwd_kernel(const float* __restrict__ w, const float* __restrict__ x,
-                                                              const float* __restrict__ dy, float scale, float lr_mul, int out_dim,
-                                                              int in_dim, float* __restrict__ d_w, float* __restrict__ d_bias,
-                                                              float* __restrict__ d_x) {
-    const int j0 = blockIdx.x * ROWS;
-    float g[ROWS];
+constexpr int kLinRows = 4;
+__device__ __forceinline__ void equal_linear_bwd_body(const float* __restrict__ w, const float* __restrict__ x,
+                                                      const float* __restrict__ dy, float scale, float lr_mul, int out_dim,
+                                                      int in_dim, float* __restrict__ d_w, float* __restrict__ d_bias,
+                                                      float* __restrict__ d_x, int blk) {
+    const int j0 = blk * kLinRows;
+    float g[kLinRows];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) g[r] = (j0 + r < out_dim) ? dy[j0 + r] : 0.f;
-    if (d_bias && threadIdx.x < ROWS && j0 + threadIdx.x < out_dim) d_bias[j0 + threadIdx.x] = lr_mul * dy[j0 + threadIdx.x];
+    for (int r = 0; r < kLinRows; ++r) g[r] = (j0 + r < out_dim) ? dy[j0 + r] : 0.f;
+    if (d_bias && threadIdx.x < kLinRows && j0 + threadIdx.x < out_dim) d_bias[j0 + threadIdx.x] = lr_mul * dy[j0 + threadIdx.x];
     for (int i = threadIdx.x; i < in_dim; i += blockDim.x) {
         const float xi = x[i];
         float acc = 0.f;
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
+        for (int r = 0; r < kLinRows; ++r) {
             if (j0 + r < out_dim) {
                 const size_t o = (size_t)(j0 + r) * in_dim + i;
                 acc += w[o] * g[r];
@@ -632,6 +603,38 @@ __global__ void __launch_bounds__(256) equal_linear_bwd_kernel(const float* __re
         }
         if (d_x) atomicAdd(&d_x[i], scale * acc);
     }
+}
+
+__global__ void __launch_bounds__(256) equal_linear_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                              const float* __restrict__ x, float scale, float lr_mul, int out_dim,
+                                                              int in_dim, float* __restrict__ y) {
+    equal_linear_fwd_body(w, bias, x, scale, lr_mul, out_dim, in_dim, y, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) equal_linear_bwd_kernel(const float* __restrict__ w, const float* __restrict__ x,
+                                                              const float* __restrict__ dy, float scale, float lr_mul, int out_dim,
+                                                              int in_dim, float* __restrict__ d_w, float* __restrict__ d_bias,
+                                                              float* __restrict__ d_x) {
+    equal_linear_bwd_body(w, x, dy, scale, lr_mul, out_dim, in_dim, d_w, d_bias, d_x, blockIdx.x);
+}
+
+// Grouped form (all modulation layers of a U-Net in one launch), descriptors as kernel parameters like ModGroup.
+constexpr int kLinGroup = 40;
+struct LinEntry {
+    const float* w; const float* bias; const float* x; const float* dy;
+    float* y; float* d_w; float* d_bias; float* d_x;
+    float scale, lr_mul; int out_dim, in_dim, block_begin, pad_;
+};
+struct LinGroup { LinEntry e[kLinGroup]; int count; };
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256) equal_linear_group_kernel(const __grid_constant__ LinGroup g) {
+    int e = 0;
+    while (e + 1 < g.count && (int)blockIdx.x >= g.e[e + 1].block_begin) ++e;
+    const LinEntry& L = g.e[e];
+    const int blk = blockIdx.x - L.block_begin;
+    if (BACKWARD) equal_linear_bwd_body(L.w, L.x, L.dy, L.scale, L.lr_mul, L.out_dim, L.in_dim, L.d_w, L.d_bias, L.d_x, blk);
+    else equal_linear_fwd_body(L.w, L.bias, L.x, L.scale, L.lr_mul, L.out_dim, L.in_dim, L.y, blk);
 }
 
 template <typename T>
@@ -912,9 +915,43 @@ int agr_equal_linear_backward(const float* w, const float* x, const float* dy, f
                               int32_t in_dim, float* d_w, float* d_bias, float* d_x, void* cuda_stream) {
     if (!w || !x || !dy || !d_w || out_dim < 1 || in_dim < 1) return AGR_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    constexpr int ROWS = 4;
-    equal_linear_bwd_kernel<ROWS><<<(out_dim + ROWS - 1) / ROWS, 256, 0, st>>>(w, x, dy, scale, lr_mul, out_dim, in_dim, d_w, d_bias, d_x);
+    equal_linear_bwd_kernel<<<(out_dim + kLinRows - 1) / kLinRows, 256, 0, st>>>(w, x, dy, scale, lr_mul, out_dim, in_dim, d_w, d_bias, d_x);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+static int equal_linear_group(const AgrEqualLinearItem* items, int32_t count, bool backward, cudaStream_t st) {
+    if (!items || count < 0) return AGR_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < count; ++i) {
+        const AgrEqualLinearItem& it = items[i];
+        if (!it.w || !it.x || it.out_dim < 1 || it.in_dim < 1) return AGR_ERR_INVALID_ARGUMENT;
+        if (!backward && !it.y) return AGR_ERR_INVALID_ARGUMENT;
+        if (backward && (!it.dy || !it.d_w)) return AGR_ERR_INVALID_ARGUMENT;
+    }
+    for (int base = 0; base < count; base += kLinGroup) {
+        LinGroup g;
+        g.count = count - base < kLinGroup ? count - base : kLinGroup;
+        int blocks = 0;
+        for (int i = 0; i < g.count; ++i) {
+            const AgrEqualLinearItem& it = items[base + i];
+            LinEntry& e = g.e[i];
+            e.w = it.w; e.bias = it.bias; e.x = it.x; e.dy = it.dy; e.y = it.y; e.d_w = it.d_w; e.d_bias = it.d_bias; e.d_x = it.d_x;
+            e.scale = it.scale; e.lr_mul = it.lr_mul; e.out_dim = it.out_dim; e.in_dim = it.in_dim; e.block_begin = blocks; e.pad_ = 0;
+            blocks += backward ? (it.out_dim + kLinRows - 1) / kLinRows : (it.out_dim + 7) / 8;
+        }
+        if (blocks == 0) continue;
+        if (backward) equal_linear_group_kernel<true><<<blocks, 256, 0, st>>>(g);
+        else equal_linear_group_kernel<false><<<blocks, 256, 0, st>>>(g);
+        if (cudaGetLastError() != cudaSuccess) return AGR_ERR_CUDA;
+    }
+    return AGR_OK;
+}
+
+int agr_equal_linear_group_forward(const AgrEqualLinearItem* items, int32_t count, void* cuda_stream) {
+    return equal_linear_group(items, count, false, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int agr_equal_linear_group_backward(const AgrEqualLinearItem* items, int32_t count, void* cuda_stream) {
+    return equal_linear_group(items, count, true, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int agr_modweight_forward(int32_t dtype, const float* w, const float* s, float scale, int32_t Cout, int32_t Cin, int32_t k,
@@ -922,28 +959,74 @@ int agr_modweight_forward(int32_t dtype, const float* w, const float* s, float s
     if (!w || !s || !w_out || Cout < 1 || Cin < 1 || k < 1) return AGR_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int64_t n = (int64_t)Cin * k * k;
-    if (row_fits_smem(n, w, w)) {
-        const size_t smem = (size_t)n * sizeof(float);
-        if (dtype == AGR_BF16) modweight_fwd_smem_kernel<__nv_bfloat16><<<Cout, 256, smem, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (__nv_bfloat16*)w_out, demod_out);
-        else modweight_fwd_smem_kernel<float><<<Cout, 256, smem, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (float*)w_out, demod_out);
-    } else if (dtype == AGR_BF16) modweight_fwd_kernel<__nv_bfloat16><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (__nv_bfloat16*)w_out, demod_out);
-    else modweight_fwd_kernel<float><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (float*)w_out, demod_out);
+    const bool fits = row_fits_smem(n, w, w);
+    const size_t smem = fits ? (size_t)n * sizeof(float) : 0;
+#define AGR_MW(T, SM) modweight_fwd_kernel<T, SM><<<Cout, 256, smem, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (T*)w_out, demod_out)
+    if (dtype == AGR_BF16) { if (fits) AGR_MW(__nv_bfloat16, true); else AGR_MW(__nv_bfloat16, false); }
+    else { if (fits) AGR_MW(float, true); else AGR_MW(float, false); }
+#undef AGR_MW
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 
 int agr_modweight_backward(int32_t dtype, const float* w, const float* s, float scale, int32_t Cout, int32_t Cin, int32_t k,
                            int32_t demodulate, int32_t transpose_io, const void* d_wout, const float* demod, float* d_w,
                            float* d_s, void* cuda_stream) {
-    if (!w || !s || !d_wout || !d_w || !d_s || (demodulate && !demod)) return AGR_ERR_INVALID_ARGUMENT;
+    if (!w || !s || !d_wout || !d_w || (demodulate && !demod)) return AGR_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int64_t n = (int64_t)Cin * k * k;
-    if (row_fits_smem(n, w, d_w)) {
-        const size_t smem = (size_t)n * sizeof(float);
-        if (dtype == AGR_BF16) modweight_bwd_smem_kernel<__nv_bfloat16><<<Cout, 256, smem, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const __nv_bfloat16*)d_wout, demod, d_w, d_s);
-        else modweight_bwd_smem_kernel<float><<<Cout, 256, smem, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const float*)d_wout, demod, d_w, d_s);
-    } else if (dtype == AGR_BF16) modweight_bwd_kernel<__nv_bfloat16><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const __nv_bfloat16*)d_wout, demod, d_w, d_s);
-    else modweight_bwd_kernel<float><<<Cout, 256, 0, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const float*)d_wout, demod, d_w, d_s);
+    const bool fits = row_fits_smem(n, w, d_w);
+    const size_t smem = fits ? (size_t)n * sizeof(float) : 0;
+#define AGR_MW(T, SM) modweight_bwd_kernel<T, SM><<<Cout, 256, smem, st>>>(w, s, scale, Cout, Cin, k * k, demodulate, transpose_io, (const T*)d_wout, demod, d_w, d_s)
+    if (dtype == AGR_BF16) { if (fits) AGR_MW(__nv_bfloat16, true); else AGR_MW(__nv_bfloat16, false); }
+    else { if (fits) AGR_MW(float, true); else AGR_MW(float, false); }
+#undef AGR_MW
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+static int modweight_group(int32_t dtype, const AgrModWeightItem* items, int32_t count, bool backward, cudaStream_t st) {
+    if (!items || count < 0) return AGR_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < count; ++i) {
+        const AgrModWeightItem& it = items[i];
+        if (!it.w || !it.s || it.Cout < 1 || it.Cin < 1 || it.k < 1) return AGR_ERR_INVALID_ARGUMENT;
+        if (!backward && !it.w_out) return AGR_ERR_INVALID_ARGUMENT;
+        if (backward && (!it.d_wout || !it.d_w || (it.demodulate && !it.demod))) return AGR_ERR_INVALID_ARGUMENT;
+    }
+    for (int base = 0; base < count; base += kModGroup) {
+        ModGroup g;
+        g.count = count - base < kModGroup ? count - base : kModGroup;
+        int blocks = 0;
+        size_t smem = 0;
+        for (int i = 0; i < g.count; ++i) {
+            const AgrModWeightItem& it = items[base + i];
+            ModEntry& e = g.e[i];
+            const int64_t n = (int64_t)it.Cin * it.k * it.k;
+            const bool fits = row_fits_smem(n, it.w, backward ? (const void*)it.d_w : (const void*)it.w);
+            e.w = it.w; e.s = it.s; e.demod_in = it.demod; e.demod_out = it.demod; e.d_wout = it.d_wout; e.w_out = it.w_out;
+            e.d_w = it.d_w; e.d_s = it.d_s; e.scale = it.scale; e.Cout = it.Cout; e.Cin = it.Cin; e.kk = it.k * it.k;
+            e.flags = (it.demodulate ? 1 : 0) | (it.transpose_io ? 2 : 0) | (fits ? 4 : 0);
+            e.block_begin = blocks;
+            blocks += it.Cout;
+            if (fits && (size_t)n * sizeof(float) > smem) smem = (size_t)n * sizeof(float);
+        }
+        if (blocks == 0) continue;
+        if (dtype == AGR_BF16) {
+            if (backward) modweight_group_kernel<__nv_bfloat16, true><<<blocks, 256, smem, st>>>(g);
+            else modweight_group_kernel<__nv_bfloat16, false><<<blocks, 256, smem, st>>>(g);
+        } else {
+            if (backward) modweight_group_kernel<float, true><<<blocks, 256, smem, st>>>(g);
+            else modweight_group_kernel<float, false><<<blocks, 256, smem, st>>>(g);
+        }
+        if (cudaGetLastError() != cudaSuccess) return AGR_ERR_CUDA;
+    }
+    return AGR_OK;
+}
+
+int agr_modweight_group_forward(int32_t dtype, const AgrModWeightItem* items, int32_t count, void* cuda_stream) {
+    return modweight_group(dtype, items, count, false, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int agr_modweight_group_backward(int32_t dtype, const AgrModWeightItem* items, int32_t count, void* cuda_stream) {
+    return modweight_group(dtype, items, count, true, static_cast<cudaStream_t>(cuda_stream));
 }
 
 }  // extern "C"

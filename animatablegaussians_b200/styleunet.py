@@ -197,7 +197,7 @@ class StyledConv(nn.Module):
 
     def forward(self, x, style, noise=None):
         c = self.conv
-        s = c.modulation(style)
+        s = lambda: c.modulation(style)   # only evaluated outside a weight plan
         if noise is None:  # randomize_noise=True path of the reference (dual_styleunet.py:309-313)
             h = x.shape[2] * (2 if c.upsample else 1)
             noise = x.new_empty(1, 1, h, h).normal_()
@@ -220,7 +220,7 @@ class ToRGB(nn.Module):
 
     def forward(self, x, style, skip=None):
         c = self.conv
-        out = ops.modulated_conv2d(x, c.weight, c.modulation(style), c.scale, demodulate=False, padding=0,
+        out = ops.modulated_conv2d(x, c.weight, lambda: c.modulation(style), c.scale, demodulate=False, padding=0,
                                    act_bias=self.bias.view(-1), activate=False)
         if skip is not None:
             out = out + ops.wavelet_upsample(skip, self.upsample.kernel)  # dwt(upsample(iwt(skip)))
@@ -357,6 +357,35 @@ class DualStyleUNet(nn.Module):
             return out, skip
         return self.iwt(skip)
 
+    def weight_plan(self, latent):
+        """Conv-ready operands of EVERY layer for this latent, prepared by the grouped kernels (a few launches instead
+        of one per layer): encoder / combiner equalised convs (scale only) and the two decoders' modulated convs
+        (style modulation of latent[:, i] as _decode indexes it).  Only for the single-style case the avatar runs."""
+        if latent.shape[0] != 1 or not latent.is_cuda:
+            return None
+        entries = []
+
+        def plain(layer):   # ConvLayer: [Blur,] EqualConv2d [, FusedLeakyReLU]
+            conv = layer[1] if layer.has_blur else layer[0]
+            entries.append((conv.weight, None, conv.scale, False, False))
+
+        plain(self.conv_in)
+        for from_rgb, cond_conv in zip(self.from_rgbs, self.cond_convs):
+            plain(from_rgb.conv); plain(cond_conv.conv1); plain(cond_conv.conv2)
+        for comb in self.comb_convs:
+            plain(comb)
+        mods = []   # (ModulatedConv2d, latent index) in _decode's order
+        for convs, rgbs in ((self.convs1, self.to_rgbs1), (self.convs2, self.to_rgbs2)):
+            mods += [(sc.conv, i) for i, sc in enumerate(convs)]
+            mods += [(rgb.conv, 2 * lvl + 2) for lvl, rgb in enumerate(rgbs)]
+        if latent.dtype == torch.float32 and latent.dim() == 3:
+            styles = ops.equal_linear_group(latent, [(c.modulation, i) for c, i in mods])
+        else:
+            styles = [c.modulation(latent[:, i]) for c, i in mods]
+        for (c, _), s in zip(mods, styles):
+            entries.append((c.weight, s, c.scale, c.demodulate, c.upsample))
+        return ops.prepare_weights(entries, ops.compute_dtype())
+
     # ------------------------------------------------------------------ reference-shaped forward
     def forward(self, styles, condition_img, cond=None, return_latents=False, inject_index=None, truncation=1,
                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True, view_feature1=None,
@@ -366,9 +395,10 @@ class DualStyleUNet(nn.Module):
         if noise is None:
             noise = [None] * self.num_layers if randomize_noise else [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
         x = ops.to_compute(condition_img)
-        cond_list = self.encode(x)
-        image1 = self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, view_feature1)
-        image2 = self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, view_feature2)
+        with ops.weight_plan(self.weight_plan(latent)):
+            cond_list = self.encode(x)
+            image1 = self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, view_feature1)
+            image2 = self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, view_feature2)
         images = ops.from_compute(torch.cat([image1, image2], 1))
         return (images, latent) if return_latents else (images, None)
 
@@ -377,9 +407,10 @@ class DualStyleUNet(nn.Module):
         compute dtype / NHWC — what AvatarNet's fused gather consumes (no channel cat, no fp32 NCHW copy)."""
         latent = self._latent(styles, False, 1, None, None)
         noise = [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
-        cond_list = self.encode(ops.to_compute(condition_img))
-        return (self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, view_feature1),
-                self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, view_feature2))
+        with ops.weight_plan(self.weight_plan(latent)):
+            cond_list = self.encode(ops.to_compute(condition_img))
+            return (self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, view_feature1),
+                    self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, view_feature2))
 
     # ------------------------------------------------------------------ view-batch split (exact)
     def forward_prefix(self, styles, condition_img):
@@ -387,11 +418,13 @@ class DualStyleUNet(nn.Module):
         level `view_level` (the addition of the view feature happens at the START of the tail)."""
         latent = self._latent(styles, False, 1, None, None)
         noise = [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
-        cond_list = self.encode(ops.to_compute(condition_img))
-        stop = self.view_level + 2
-        s1 = self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, None, stop=stop)
-        s2 = self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, None, stop=stop)
-        return dict(latent=latent, noise=noise, cond_list=cond_list, s1=s1, s2=s2)
+        plan = self.weight_plan(latent)
+        with ops.weight_plan(plan):
+            cond_list = self.encode(ops.to_compute(condition_img))
+            stop = self.view_level + 2
+            s1 = self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, None, stop=stop)
+            s2 = self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, None, stop=stop)
+        return dict(latent=latent, noise=noise, cond_list=cond_list, s1=s1, s2=s2, plan=plan)
 
     def forward_view_tail(self, prefix, view_feature1, view_feature2, as_pair=False):
         """View-dependent remainder for a BATCH of V views (view features (V,128,h,w)): add the (bilinearly resized)
@@ -408,8 +441,9 @@ class DualStyleUNet(nn.Module):
                 out = ops.expand_batch(out, V)
             if V > 1 and skip is not None:
                 skip = ops.expand_batch(skip, V)
-            outs.append(self._decode(convs, rgbs, prefix["cond_list"], prefix["latent"], prefix["noise"], None,
-                                     start=self.view_level + 2, state=(out, skip)))
+            with ops.weight_plan(prefix.get("plan")):
+                outs.append(self._decode(convs, rgbs, prefix["cond_list"], prefix["latent"], prefix["noise"], None,
+                                         start=self.view_level + 2, state=(out, skip)))
         if as_pair:
             return outs[0], outs[1]
         return ops.from_compute(torch.cat(outs, 1))

@@ -28,7 +28,24 @@ LIBRARY_OPS = ("conv2d wgrad, all shapes (cuDNN via torch)",
                "CUB DeviceScan + DeviceRadixSort in the rasterizer binning (as in the reference)")
 
 _p = C.c_void_p
+class AgrModWeightItem(C.Structure):
+    """include/agr_styleunet.h"""
+    _fields_ = [("w", _p), ("s", _p), ("w_out", _p), ("demod", _p), ("d_wout", _p), ("d_w", _p), ("d_s", _p),
+                ("scale", C.c_float), ("Cout", C.c_int32), ("Cin", C.c_int32), ("k", C.c_int32),
+                ("demodulate", C.c_int32), ("transpose_io", C.c_int32)]
+
+
+class AgrEqualLinearItem(C.Structure):
+    """include/agr_styleunet.h"""
+    _fields_ = [("w", _p), ("bias", _p), ("x", _p), ("dy", _p), ("y", _p), ("d_w", _p), ("d_bias", _p), ("d_x", _p),
+                ("scale", C.c_float), ("lr_mul", C.c_float), ("out_dim", C.c_int32), ("in_dim", C.c_int32)]
+
+
 _lib.register_symbols({
+    "agr_equal_linear_group_forward": (C.c_int, [C.POINTER(AgrEqualLinearItem), C.c_int32, _p]),
+    "agr_equal_linear_group_backward": (C.c_int, [C.POINTER(AgrEqualLinearItem), C.c_int32, _p]),
+    "agr_modweight_group_forward": (C.c_int, [C.c_int32, C.POINTER(AgrModWeightItem), C.c_int32, _p]),
+    "agr_modweight_group_backward": (C.c_int, [C.c_int32, C.POINTER(AgrModWeightItem), C.c_int32, _p]),
     "agr_upfirdn2d": (C.c_int, [C.c_int32, _p, _p] + [C.c_int32] * 6 + [C.POINTER(C.c_float)] + [C.c_int32] * 6 + [_p]),
     "agr_haar": (C.c_int, [C.c_int32, C.c_int32, _p, _p] + [C.c_int32] * 4 + [_p]),
     "agr_bias_act_forward": (C.c_int, [C.c_int32, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, _p]),
@@ -494,6 +511,122 @@ class _ModWeight(torch.autograd.Function):
         return dw.view(wshape), ds.view(sshape), None, None, None, None
 
 
+def _addr(t):
+    return None if t is None else t.data_ptr()
+
+
+class _ModWeightGroup(torch.autograd.Function):
+    """_ModWeight for every conv layer of a U-Net at once (agr_modweight_group_*): `specs[l] = (scale, demodulate,
+    transpose_io)`, `tensors = (weight_0, s_0, weight_1, s_1, ...)` with s_l = None for a plain equalised conv."""
+
+    @staticmethod
+    def forward(ctx, specs, dtype, *tensors):
+        lib = _lib.load()
+        L = len(specs)
+        ws = [tensors[2 * l].detach().float().contiguous() for l in range(L)]
+        dev = ws[0].device
+        svs, outs, demods = [], [], []
+        items = (AgrModWeightItem * L)()
+        for l, (scale, demodulate, transpose_io) in enumerate(specs):
+            w, s = ws[l], tensors[2 * l + 1]
+            Cout, Cin, k = w.shape[-4], w.shape[-3], w.shape[-1]
+            sv = _ones(Cin, dev) if s is None else s.detach().float().contiguous().view(-1)
+            shape = (Cin, Cout, k, k) if transpose_io else (Cout, Cin, k, k)
+            out = torch.empty(shape, dtype=dtype, device=dev, memory_format=_CL)
+            demod = torch.empty(Cout, dtype=torch.float32, device=dev) if demodulate else None
+            svs.append(sv); outs.append(out); demods.append(demod)
+            it = items[l]
+            it.w, it.s, it.w_out, it.demod = w.data_ptr(), sv.data_ptr(), out.data_ptr(), _addr(demod)
+            it.scale, it.Cout, it.Cin, it.k = float(scale), Cout, Cin, k
+            it.demodulate, it.transpose_io = int(bool(demodulate)), int(bool(transpose_io))
+        with torch.cuda.device(dev), stats.stage("styleunet_weight", launches=(L + 39) // 40):
+            _check(lib.agr_modweight_group_forward(_code(outs[0]), items, L, _stream(ws[0])), "agr_modweight_group_forward")
+        ctx.save_for_backward(*ws, *svs, *[d for d in demods if d is not None])
+        ctx.meta = (specs, [d is not None for d in demods], [tensors[2 * l].shape for l in range(L)],
+                    [None if tensors[2 * l + 1] is None else tensors[2 * l + 1].shape for l in range(L)], dtype)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        lib = _lib.load()
+        specs, has_demod, wshapes, sshapes, dtype = ctx.meta
+        L = len(specs)
+        saved = ctx.saved_tensors
+        ws, svs, rest = saved[:L], saved[L:2 * L], list(saved[2 * L:])
+        dev = ws[0].device
+        items = (AgrModWeightItem * L)()
+        keep, grads = [], [None, None]
+        for l, (scale, demodulate, transpose_io) in enumerate(specs):
+            w = ws[l]
+            Cout, Cin, k = w.shape[-4], w.shape[-3], w.shape[-1]
+            demod = rest.pop(0) if has_demod[l] else None
+            g = gs[l]
+            if g is None:   # a layer this forward never used
+                shape = (Cin, Cout, k, k) if transpose_io else (Cout, Cin, k, k)
+                g = torch.zeros(shape, dtype=dtype, device=dev)
+            g = g.contiguous(memory_format=_CL)
+            dw = torch.empty_like(w)
+            ds = _zeros(Cin, dev) if sshapes[l] is not None and ctx.needs_input_grad[3 + 2 * l] else None
+            keep.append((g, dw, ds))
+            it = items[l]
+            it.w, it.s, it.demod, it.d_wout = w.data_ptr(), svs[l].data_ptr(), _addr(demod), g.data_ptr()
+            it.d_w, it.d_s = dw.data_ptr(), _addr(ds)
+            it.scale, it.Cout, it.Cin, it.k = float(scale), Cout, Cin, k
+            it.demodulate, it.transpose_io = int(bool(demodulate)), int(bool(transpose_io))
+            grads.append(dw.view(wshapes[l]))
+            grads.append(ds.view(sshapes[l]) if ds is not None else None)
+        code = _code(keep[0][0])
+        if any(_code(k_[0]) != code for k_ in keep):
+            raise RuntimeError("modweight group: mixed gradient dtypes")
+        with torch.cuda.device(dev), stats.stage("styleunet_weight", launches=(L + 39) // 40):
+            _check(lib.agr_modweight_group_backward(code, items, L, _stream(ws[0])), "agr_modweight_group_backward")
+        return tuple(grads)
+
+
+# A "weight plan" holds the conv-ready operands of every layer of one U-Net for one step, prepared by the grouped
+# kernels; layers look their weight up by parameter identity and fall back to the per-layer op outside a plan.
+_plan = None
+
+
+@contextlib.contextmanager
+def weight_plan(plan):
+    global _plan
+    prev, _plan = _plan, plan
+    try:
+        yield
+    finally:
+        _plan = prev
+
+
+def planned_weight(weight, dtype):
+    if _plan is None:
+        return None
+    w = _plan.get(id(weight))
+    return w if w is not None and w.dtype == dtype else None
+
+
+def prepare_weights(entries, dtype):
+    """entries: [(weight parameter, style modulation s (1,Cin) or None, scale, demodulate, transpose_io)] ->
+    {id(weight): prepared operand}."""
+    if not entries:
+        return {}
+    specs = tuple((float(e[2]), bool(e[3]), bool(e[4])) for e in entries)
+    flat = []
+    for e in entries:
+        flat += [e[0], e[1]]
+    outs = _ModWeightGroup.apply(specs, dtype, *flat)
+    return {id(e[0]): o for e, o in zip(entries, outs)}
+
+
+def _prepared(weight, s, scale, demodulate, transpose_io, dtype):
+    w = planned_weight(weight, dtype)
+    if w is not None:
+        return w
+    if s is None:
+        s = _ones(weight.shape[-3], weight.device)
+    return _ModWeight.apply(weight, s, scale, demodulate, transpose_io, dtype)
+
+
 class _EqualLinearVec(torch.autograd.Function):
     """EqualLinear (no activation) on one style vector: lr_mul * bias + scale * W x, one launch each way."""
 
@@ -533,6 +666,77 @@ def equal_linear(x, weight, bias, scale, lr_mul):
     if x.is_cuda and x.dim() == 2 and x.shape[0] == 1 and x.dtype == torch.float32 and weight.dtype == torch.float32:
         return _EqualLinearVec.apply(x, weight, bias, scale, lr_mul)
     return F.linear(x, weight * scale, bias=bias * lr_mul if bias is not None else None)
+
+
+class _EqualLinearGroup(torch.autograd.Function):
+    """y_l = EqualLinear_l(latent[0, idx_l]) for every modulation layer of a U-Net in one launch each way;
+    `tensors = (weight_0, bias_0, weight_1, bias_1, ...)`, `specs[l] = (scale, lr_mul)`.  The style gradients of all
+    layers accumulate straight into one d_latent buffer."""
+
+    @staticmethod
+    def forward(ctx, latent, idx, specs, *tensors):
+        lib = _lib.load()
+        L = len(idx)
+        lat = latent.detach().float().contiguous()
+        D = lat.shape[-1]
+        dev = lat.device
+        ws = [tensors[2 * l].detach().contiguous() for l in range(L)]
+        items = (AgrEqualLinearItem * L)()
+        ys, keep = [], []
+        for l in range(L):
+            w, b = ws[l], tensors[2 * l + 1]
+            b = b.detach().contiguous() if b is not None else None
+            out_dim, in_dim = w.shape
+            if in_dim != D or w.dtype != torch.float32:
+                raise RuntimeError("equal_linear group: weight %s does not match the latent width %d" % (tuple(w.shape), D))
+            y = torch.empty(out_dim, dtype=torch.float32, device=dev)
+            ys.append(y); keep.append(b)
+            it = items[l]
+            it.w, it.bias, it.x, it.y = w.data_ptr(), _addr(b), lat.data_ptr() + 4 * D * int(idx[l]), y.data_ptr()
+            it.scale, it.lr_mul, it.out_dim, it.in_dim = float(specs[l][0]), float(specs[l][1]), out_dim, in_dim
+        with torch.cuda.device(dev), stats.stage("styleunet_weight", launches=(L + 39) // 40):
+            _check(lib.agr_equal_linear_group_forward(items, L, _stream(lat)), "agr_equal_linear_group_forward")
+        ctx.save_for_backward(lat, *ws)
+        ctx.meta = (tuple(int(i) for i in idx), specs, [tensors[2 * l + 1] is not None for l in range(L)], latent.shape)
+        return tuple(y.view(1, -1) for y in ys)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        lib = _lib.load()
+        idx, specs, has_b, lshape = ctx.meta
+        L = len(idx)
+        lat, ws = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        D = lat.shape[-1]
+        dev = lat.device
+        d_lat = _zeros(lat.numel(), dev) if ctx.needs_input_grad[0] else None
+        items = (AgrEqualLinearItem * L)()
+        keep, grads = [], [None, None, None]
+        for l in range(L):
+            w = ws[l]
+            out_dim, in_dim = w.shape
+            g = gs[l]
+            g = torch.zeros(out_dim, dtype=torch.float32, device=dev) if g is None else g.float().contiguous().view(-1)
+            dw = torch.empty_like(w)
+            db = torch.empty(out_dim, dtype=torch.float32, device=dev) if has_b[l] else None
+            keep.append(g)
+            it = items[l]
+            it.w, it.x, it.dy = w.data_ptr(), lat.data_ptr() + 4 * D * idx[l], g.data_ptr()
+            it.d_w, it.d_bias = dw.data_ptr(), _addr(db)
+            it.d_x = None if d_lat is None else d_lat.data_ptr() + 4 * D * idx[l]
+            it.scale, it.lr_mul, it.out_dim, it.in_dim = float(specs[l][0]), float(specs[l][1]), out_dim, in_dim
+            grads += [dw, db]
+        with torch.cuda.device(dev), stats.stage("styleunet_weight", launches=(L + 39) // 40):
+            _check(lib.agr_equal_linear_group_backward(items, L, _stream(lat)), "agr_equal_linear_group_backward")
+        grads[0] = d_lat.view(lshape) if d_lat is not None else None
+        return tuple(grads)
+
+
+def equal_linear_group(latent, layers):
+    """layers: [(EqualLinear-like module with weight / bias / scale / lr_mul, index into latent[0])] -> [(1, out_dim)]."""
+    flat = []
+    for m, _ in layers:
+        flat += [m.weight, m.bias]
+    return _EqualLinearGroup.apply(latent, tuple(i for _, i in layers), tuple((m.scale, m.lr_mul) for m, _ in layers), *flat)
 
 
 _ones_cache = {}
@@ -683,12 +887,12 @@ def equal_conv2d_split(a, b, weight, scale, act_bias=None, activate=True):
           _lib.load().agr_conv2d_tc_supported(a.shape[2], a.shape[3], Cb, weight.shape[0], k))
     if not ok:
         return equal_conv2d(torch.cat([a, expand_batch(b, a.shape[0])], 1), weight, scale, 1, k // 2, act_bias, activate)
-    w = _ModWeight.apply(weight, _ones(weight.shape[1], weight.device), scale, False, False, a.dtype)
+    w = _prepared(weight, None, scale, False, False, a.dtype)
     return _SplitConvAct.apply(a, b, w, act_bias, activate)
 
 
 def equal_conv2d(x, weight, scale, stride, padding, act_bias=None, activate=True):
-    w = _ModWeight.apply(weight, _ones(weight.shape[1], weight.device), scale, False, False, x.dtype)
+    w = _prepared(weight, None, scale, False, False, x.dtype)
     if _tc_ok(x, w.shape[0], w.shape[-1], stride) and padding == w.shape[-1] // 2:
         return _ConvAct.apply(x, w, act_bias, None, None, activate)
     out = F.conv2d(x, w, None, stride=stride, padding=padding)
@@ -699,9 +903,15 @@ def equal_conv2d(x, weight, scale, stride, padding, act_bias=None, activate=True
 
 def modulated_conv2d(x, weight, s, scale, demodulate=True, upsample=False, downsample=False, blur=None, padding=1,
                      noise=None, noise_weight=None, act_bias=None, activate=True):
-    if s.shape[0] != 1:
-        raise RuntimeError("one style per call: the batch (views of one pose) shares the modulated weight")
-    w = _ModWeight.apply(weight, s, scale, demodulate, upsample, x.dtype)
+    """`s` may be a callable returning the (1, Cin) style modulation: it is only evaluated when no weight plan holds
+    this layer's operand."""
+    w = planned_weight(weight, x.dtype)
+    if w is None:
+        if callable(s):
+            s = s()
+        if s.shape[0] != 1:
+            raise RuntimeError("one style per call: the batch (views of one pose) shares the modulated weight")
+        w = _ModWeight.apply(weight, s, scale, demodulate, upsample, x.dtype)
     if upsample:
         out = blur(F.conv_transpose2d(x, w, padding=0, stride=2))
     elif downsample:

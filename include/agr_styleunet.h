@@ -59,10 +59,28 @@ int agr_modweight_forward(int32_t dtype, const float* w, const float* s, float s
                           int32_t k, int32_t demodulate, int32_t transpose_io, void* w_out, float* demod_out,
                           void* cuda_stream);
 /* Backward: d_wout (same layout/dtype as w_out) -> d_w (Cout,Cin,k,k) fp32 (overwritten) and d_s (Cin) fp32
- * (ACCUMULATED; caller zeroes). */
+ * (ACCUMULATED; caller zeroes; NULL = not wanted). */
 int agr_modweight_backward(int32_t dtype, const float* w, const float* s, float scale, int32_t Cout, int32_t Cin,
                            int32_t k, int32_t demodulate, int32_t transpose_io, const void* d_wout,
                            const float* demod, float* d_w, float* d_s, void* cuda_stream);
+
+/* Grouped form of the two calls above: all conv layers of a U-Net (modulated and plain equalised ones, the latter with
+ * s = ones and demodulate = 0) in ceil(count / 40) launches.  `items` is a HOST array; every pointer in it is a device
+ * pointer with the meaning of the same-named argument above.  forward reads w, s and writes w_out, demod;
+ * backward reads w, s, demod, d_wout and writes d_w, accumulates d_s (d_s may be NULL: no style gradient wanted). */
+typedef struct AgrModWeightItem {
+    const float* w;
+    const float* s;
+    void* w_out;
+    float* demod;
+    const void* d_wout;
+    float* d_w;
+    float* d_s;
+    float scale;
+    int32_t Cout, Cin, k, demodulate, transpose_io;
+} AgrModWeightItem;
+int agr_modweight_group_forward(int32_t dtype, const AgrModWeightItem* items, int32_t count, void* cuda_stream);
+int agr_modweight_group_backward(int32_t dtype, const AgrModWeightItem* items, int32_t count, void* cuda_stream);
 
 /* ---- dense contraction on the tensor cores (tcgen05.mma + TMA, bf16 in / fp32 accumulate / bf16 out) ----
  * Stride-1 "same" convolution, NHWC, N images sharing one weight (the view batch of the colour-net tail):
@@ -123,6 +141,24 @@ int agr_equal_linear_forward(const float* w, const float* bias, const float* x, 
                              int32_t in_dim, float* y, void* cuda_stream);
 int agr_equal_linear_backward(const float* w, const float* x, const float* dy, float scale, float lr_mul, int32_t out_dim,
                               int32_t in_dim, float* d_w, float* d_bias, float* d_x, void* cuda_stream);
+
+/* Grouped form: every modulation layer of a U-Net in ceil(count / 40) launches.  `items` is a HOST array of device
+ * pointers with the meaning of the same-named arguments above; several items may share one d_x (their contributions
+ * are accumulated). */
+typedef struct AgrEqualLinearItem {
+    const float* w;
+    const float* bias;
+    const float* x;
+    const float* dy;
+    float* y;
+    float* d_w;
+    float* d_bias;
+    float* d_x;
+    float scale, lr_mul;
+    int32_t out_dim, in_dim;
+} AgrEqualLinearItem;
+int agr_equal_linear_group_forward(const AgrEqualLinearItem* items, int32_t count, void* cuda_stream);
+int agr_equal_linear_group_backward(const AgrEqualLinearItem* items, int32_t count, void* cuda_stream);
 
 /* w_out[ci][k*k-1-t][co] = w_krsc[co][t][ci]  (bf16) */
 int agr_weight_flip_transpose(const void* w_krsc, void* w_out, int32_t Cout, int32_t Cin, int32_t ksize, void* cuda_stream);

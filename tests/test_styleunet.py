@@ -376,3 +376,73 @@ def test_wavelet_upsample_banks_reproduce_the_chain():
             dx[:, :, m, n] = np.einsum("ioab,ocab->ic", a, gp[:, :, 2 * m:2 * m + 4, 2 * n:2 * n + 4])
     assert np.abs(out.reshape(1, 4 * Ci, 2 * h, 2 * w) - y.detach().numpy()).max() < 1e-12
     assert np.abs(dx.reshape(1, 4 * Ci, h, w) - x.grad.numpy()).max() < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_grouped_modweight_equals_per_layer(dtype, built_lib):
+    """agr_modweight_group_* (all layers of a net in ceil(L/40) launches) against the per-layer op: identical operands
+    and weight gradients (same row bodies), style gradients up to atomic-add order.  45 layers -> two launches."""
+    from animatablegaussians_b200 import styleunet_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shapes = [(64, 32, 3, True, False, True), (12, 64, 1, False, False, True), (32, 48, 3, True, True, True),
+              (16, 3, 3, False, False, False), (8, 2048, 3, True, False, True), (128, 128, 3, False, False, False),
+              (16, 1024, 3, True, True, True), (5, 7, 1, True, False, True)]
+    shapes = (shapes * 6)[:45]
+    entries, ref = [], []
+    for Cout, Cin, k, demod, tr, styled in shapes:
+        w = torch.randn(1, Cout, Cin, k, k, device="cuda", generator=g).requires_grad_(True)
+        s = (1 + 0.3 * torch.randn(1, Cin, device="cuda", generator=g)).requires_grad_(True) if styled else None
+        scale = 1 / (Cin * k * k) ** 0.5
+        entries.append((w, s, scale, demod, tr))
+        w2 = w.detach().clone().requires_grad_(True)
+        s2 = s.detach().clone().requires_grad_(True) if styled else None
+        ref.append((w2, s2, scale, demod, tr))
+    with ops.step_arena():
+        plan = ops.prepare_weights(entries, dtype)
+        outs = [plan[id(e[0])] for e in entries]
+        singles = [ops._ModWeight.apply(w, s if s is not None else torch.ones(1, w.shape[2], device="cuda"), scale, demod, tr, dtype)
+                   for w, s, scale, demod, tr in ref]
+        ups = [torch.randn(o.shape, device="cuda", generator=g).to(dtype) for o in outs]
+        torch.autograd.backward(outs, ups)
+        torch.autograd.backward(singles, ups)
+    for (w, s, *_), (w2, s2, *_), o, o2 in zip(entries, ref, outs, singles):
+        assert torch.equal(o, o2)
+        assert torch.equal(w.grad, w2.grad)
+        if s is not None:
+            _cmp(s.grad, s2.grad, 1e-5)
+
+
+@pytest.mark.gpu
+def test_grouped_equal_linear_equals_per_layer(built_lib):
+    """agr_equal_linear_group_* against the per-layer op on slices of one latent; 43 layers -> two launches; the style
+    gradients of all layers land in one d_latent."""
+    from animatablegaussians_b200 import styleunet_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(12)
+    D, n_lat = 96, 7
+
+    class Lin:
+        def __init__(self, out_dim, bias, lr_mul):
+            self.weight = torch.randn(out_dim, D, device="cuda", generator=g).requires_grad_(True)
+            self.bias = torch.randn(out_dim, device="cuda", generator=g).requires_grad_(True) if bias else None
+            self.scale, self.lr_mul = lr_mul / D ** 0.5, lr_mul
+
+    layers = [(Lin(o, b, lr), i % n_lat) for i, (o, b, lr) in enumerate([(64, True, 1.0), (5, False, 0.5), (130, True, 1.0), (32, True, 0.01)] * 11)][:43]
+    lat = torch.randn(1, n_lat, D, device="cuda", generator=g).requires_grad_(True)
+    lat2 = lat.detach().clone().requires_grad_(True)
+    with ops.step_arena():
+        ys = ops.equal_linear_group(lat, layers)
+        ups = [torch.randn(1, m.weight.shape[0], device="cuda", generator=g) for m, _ in layers]
+        torch.autograd.backward(ys, ups)
+        grads = [(m.weight.grad.clone(), None if m.bias is None else m.bias.grad.clone()) for m, _ in layers]
+        for m, _ in layers:
+            m.weight.grad = None
+            if m.bias is not None:
+                m.bias.grad = None
+        ys2 = [ops.equal_linear(lat2[:, i], m.weight, m.bias, m.scale, m.lr_mul) for m, i in layers]
+        torch.autograd.backward(ys2, ups)
+    for (m, _), y, y2, (gw, gb) in zip(layers, ys, ys2, grads):
+        assert torch.equal(y, y2) and torch.equal(gw, m.weight.grad)
+        if gb is not None:
+            assert torch.equal(gb, m.bias.grad)
+    _cmp(lat.grad, lat2.grad, 1e-5)
