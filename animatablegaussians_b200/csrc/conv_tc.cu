@@ -102,6 +102,8 @@ struct ConvParams {
     const float* residual;  // (H, W, Cout) fp32 added before bias/activation, shared by the N images; or null
     float* y_f32;           // when set, the result is stored in fp32 here instead of bf16 in y (partial sums)
     int w_cin_offset;      // first input channel of the weight slice this call contracts with (split-K over a concat)
+    int splits;            // > 1: blockIdx.z owns a contiguous slice of the (tap, channel-block) loop and ADDS its fp32
+                           // partial tile into y_f32 (zeroed by the caller); bias / noise / activation run in conv_finish_kernel
     int activate;
     __nv_bfloat16* y;      // (H, W, Cout)
 };
@@ -124,7 +126,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int h0 = (tile_m / tiles_w) * TILE_H, w0 = (tile_m % tiles_w) * TILE_W;
     const int n0 = blockIdx.y * BN;
     const int kchunks = p.Cin / BK;
-    const int num_kb = p.taps * kchunks;
+    const int num_kb_all = p.taps * kchunks;
+    const int kb0 = p.splits > 1 ? (int)(((long)blockIdx.z * num_kb_all) / p.splits) : 0;
+    const int kb1 = p.splits > 1 ? (int)(((long)(blockIdx.z + 1) * num_kb_all) / p.splits) : num_kb_all;
+    const int num_kb = kb1 - kb0;   // >= 1: the host keeps splits <= num_kb_all
     const int pad = p.ksize / 2;
 
     if (threadIdx.x == 0) {
@@ -146,10 +151,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (warp == 0) {
         // ================= TMA producer (one elected lane) =================
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+            for (int it = 0; it < num_kb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
+                const int kb = kb0 + it;
                 const int tap = kb / kchunks, ck = kb - tap * kchunks;
                 const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
                 unsigned char* a_dst = smem + s * STAGE_BYTES;
@@ -163,9 +169,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // ================= MMA issuer (one elected lane) =================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(BM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+            for (int it = 0; it < num_kb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
@@ -173,7 +179,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(b_addr);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 B -> +2 in the (>>4) start-address field
-                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
                 umma_commit(&empty_bar[s]);      // frees the smem stage once these MMAs have read it
             }
             umma_commit(&tmem_full_bar);         // accumulator complete
@@ -207,6 +213,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + rr.w);
                 }
             }
+            if (p.splits > 1) {   // split-K partial tile: accumulate into the zeroed fp32 workspace
+#pragma unroll
+                for (int i = 0; i < 32; ++i) atomicAdd(out32 + c0 + i, __uint_as_float(r[i]));
+                continue;
+            }
             if (out32) {   // fp32 partial result (no epilogue math): consumed as `residual` by the second half
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -234,6 +245,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    }
+}
+
+// ---- split-K finish: y = act(acc + noise_w * noise + bias) in bf16 from the fp32 accumulation buffer
+__global__ void __launch_bounds__(256) conv_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ y, long pixels,
+                                                         long pixels_per_image, int Cout, const float* __restrict__ bias,
+                                                         const float* __restrict__ noise, const float* __restrict__ noise_w,
+                                                         int activate) {
+    const int cv = Cout / 8;
+    const long total = pixels * cv;
+    const float nw = (noise && noise_w) ? noise_w[0] : 0.f;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cv) * 8;
+        const long p = idx / cv;
+        const float add = noise ? nw * noise[p % pixels_per_image] : 0.f;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(acc + p * Cout + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(acc + p * Cout + c + 4));
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint4 packed;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&packed);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float t = v[i] + add;
+            if (bias) t += bias[c + i];
+            if (activate) t = (t > 0.f ? t : 0.2f * t) * 1.4142135623730951f;
+            v[i] = t;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(y + p * Cout + c) = packed;
     }
 }
 
@@ -302,7 +343,7 @@ static int launch_s(const CUtensorMap& mx, const CUtensorMap& mw, const ConvPara
         if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
         attr = true;
     }
-    dim3 grid(p.N * (p.H / TILE_H) * (p.W / TILE_W), p.Cout / BN);
+    dim3 grid(p.N * (p.H / TILE_H) * (p.W / TILE_W), p.Cout / BN, p.splits > 1 ? p.splits : 1);
     conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, s>>>(mx, mw, p);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
@@ -312,7 +353,7 @@ static int launch(const void* x, const void* w, const ConvParams& p, int w_cin_t
     CUtensorMap mx, mw;
     if (!make_map_4d(&mx, x, (uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N, BK, TILE_W, TILE_H)) return AGR_ERR_CUDA;
     if (!make_map_3d(&mw, w, (uint64_t)w_cin_total, (uint64_t)p.taps, (uint64_t)p.Cout, BK, 1, BN)) return AGR_ERR_CUDA;
-    const long tiles = (long)p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN);
+    const long tiles = (long)p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN) * (p.splits > 1 ? p.splits : 1);
     if (BN == 64 || tiles <= 148) return launch_s<BN, 4>(mx, mw, p, s);
     return launch_s<BN, 3>(mx, mw, p, s);
 }
@@ -339,10 +380,44 @@ int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t N,
     ConvParams p;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
     p.bias = bias; p.noise = noise; p.noise_w = noise_w; p.activate = activate; p.y = static_cast<__nv_bfloat16*>(y);
-    p.residual = nullptr; p.y_f32 = nullptr; p.w_cin_offset = 0;
+    p.residual = nullptr; p.y_f32 = nullptr; p.w_cin_offset = 0; p.splits = 1;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     if (Cout % 128 == 0) return launch<128>(x, w_krsc, p, Cin, s);
     return launch<64>(x, w_krsc, p, Cin, s);
+}
+
+int agr_conv2d_tc_splits(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize) {
+    using namespace agr::tc;
+    if (!agr_conv2d_tc_supported(H, W, Cin, Cout, ksize)) return 1;
+    const int BN = (Cout % 128 == 0) ? 128 : 64;
+    const long tiles = (long)N * (H / TILE_H) * (W / TILE_W) * (Cout / BN);
+    const int num_kb = ksize * ksize * (Cin / BK);
+    // fill ~2 CTAs per SM, but keep >= 4 (tap, channel-block) steps per CTA so the pipeline still overlaps
+    long s = (2 * 148) / tiles;
+    if (s > num_kb / 4) s = num_kb / 4;
+    if (s > 32) s = 32;
+    return s < 2 ? 1 : (int)s;
+}
+
+int agr_conv2d_tc_forward_splitk(const void* x, const void* w_krsc, void* y, float* workspace, int32_t splits, int32_t N, int32_t H,
+                                 int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, const float* bias, const float* noise,
+                                 const float* noise_w, int32_t activate, void* cuda_stream) {
+    using namespace agr::tc;
+    if (!x || !w_krsc || !y || !workspace || N < 1 || !agr_conv2d_tc_supported(H, W, Cin, Cout, ksize)) return AGR_ERR_INVALID_ARGUMENT;
+    if (splits < 2 || splits > ksize * ksize * (Cin / BK)) return AGR_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const long pixels = (long)N * H * W;
+    if (cudaMemsetAsync(workspace, 0, (size_t)pixels * Cout * sizeof(float), s) != cudaSuccess) return AGR_ERR_CUDA;
+    ConvParams p;
+    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
+    p.bias = nullptr; p.noise = nullptr; p.noise_w = nullptr; p.activate = 0; p.y = nullptr;
+    p.residual = nullptr; p.y_f32 = workspace; p.w_cin_offset = 0; p.splits = splits;
+    const int st = (Cout % 128 == 0) ? launch<128>(x, w_krsc, p, Cin, s) : launch<64>(x, w_krsc, p, Cin, s);
+    if (st != AGR_OK) return st;
+    const long total = pixels * (Cout / 8);
+    long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
+    conv_finish_kernel<<<(unsigned)g, 256, 0, s>>>(workspace, static_cast<__nv_bfloat16*>(y), pixels, (long)H * W, Cout, bias, noise, noise_w, activate);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 
 int agr_conv2d_tc_forward_split(const void* x, const void* w_krsc, void* y, int32_t out_fp32, int32_t N, int32_t H, int32_t W,
@@ -356,7 +431,7 @@ int agr_conv2d_tc_forward_split(const void* x, const void* w_krsc, void* y, int3
     p.bias = bias; p.noise = nullptr; p.noise_w = nullptr; p.activate = activate;
     p.y = out_fp32 ? nullptr : static_cast<__nv_bfloat16*>(y);
     p.y_f32 = out_fp32 ? static_cast<float*>(y) : nullptr;
-    p.residual = residual; p.w_cin_offset = w_cin_offset;
+    p.residual = residual; p.w_cin_offset = w_cin_offset; p.splits = 1;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     if (Cout % 128 == 0) return launch<128>(x, w_krsc, p, w_cin_total, s);
     return launch<64>(x, w_krsc, p, w_cin_total, s);

@@ -54,6 +54,8 @@ _lib.register_symbols({
     "agr_modweight_backward": (C.c_int, [C.c_int32, _p, _p, C.c_float] + [C.c_int32] * 5 + [_p, _p, _p, _p, _p]),
     "agr_conv2d_tc_supported": (C.c_int, [C.c_int32] * 5),
     "agr_conv2d_tc_forward": (C.c_int, [_p, _p, _p] + [C.c_int32] * 6 + [_p, _p, _p, C.c_int32, _p]),
+    "agr_conv2d_tc_splits": (C.c_int, [C.c_int32] * 6),
+    "agr_conv2d_tc_forward_splitk": (C.c_int, [_p, _p, _p, _p] + [C.c_int32] * 7 + [_p, _p, _p, C.c_int32, _p]),
     "agr_weight_flip_transpose": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
     "agr_sum_batch": (C.c_int, [C.c_int32, _p, _p, C.c_int32, C.c_int64, _p]),
     "agr_bilinear2x_add_forward": (C.c_int, [C.c_int32, _p, _p, _p] + [C.c_int32] * 5 + [_p]),
@@ -66,6 +68,8 @@ _lib.register_symbols({
 
 _COMPUTE_DTYPE = torch.float32
 _CL = torch.channels_last
+import os as _os  # noqa: E402
+_SPLITK = _os.environ.get("AGR_CONV_SPLITK", "1") != "0"   # r01 measurement switch (tools/validate_gpu.sh); to be removed
 
 
 def set_compute_dtype(dtype):
@@ -761,8 +765,16 @@ def _tc_conv(x, w, Cout, k, bias, noise, noise_w, activate):
     lib = _lib.load()
     y = _new_like(x, Cout, x.shape[2], x.shape[3])
     stats.add_work("styleunet_conv_tc", 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * x.shape[1] * Cout * k * k)
+    N, Cin, H, W = x.shape
+    splits = lib.agr_conv2d_tc_splits(N, H, W, Cin, Cout, k) if _SPLITK else 1
+    if splits > 1:   # coarse levels: a handful of output tiles, long contraction -> split-K over the idle SMs
+        ws = torch.empty(N * H * W * Cout, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=2):
+            _check(lib.agr_conv2d_tc_forward_splitk(_ptr(x), _ptr(w), _ptr(y), _ptr(ws), splits, N, H, W, Cin, Cout, k, _ptr(bias),
+                                                    _ptr(noise), _ptr(noise_w), int(activate), _stream(x)), "agr_conv2d_tc_forward_splitk")
+        return y
     with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=1):
-        _check(lib.agr_conv2d_tc_forward(_ptr(x), _ptr(w), _ptr(y), x.shape[0], x.shape[2], x.shape[3], x.shape[1], Cout, k, _ptr(bias),
+        _check(lib.agr_conv2d_tc_forward(_ptr(x), _ptr(w), _ptr(y), N, H, W, Cin, Cout, k, _ptr(bias),
                                          _ptr(noise), _ptr(noise_w), int(activate), _stream(x)), "agr_conv2d_tc_forward")
     return y
 

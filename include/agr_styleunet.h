@@ -93,6 +93,15 @@ int agr_conv2d_tc_supported(int32_t H, int32_t W, int32_t Cin, int32_t Cout, int
 int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin,
                           int32_t Cout, int32_t ksize, const float* bias, const float* noise, const float* noise_w,
                           int32_t activate, void* cuda_stream);
+/* Split-K form for the coarse decoder levels (16x16 ... 64x64 maps with 512 channels: 2-128 output tiles, one CTA each
+ * walking up to 72 (tap, channel-block) steps -- latency-bound at ~33 us on 2-128 of the 148 SMs).  `splits` CTAs share an
+ * output tile, each contracting a contiguous slice of the (tap, channel-block) loop and adding its fp32 partial tile
+ * into `workspace` (N*H*W*Cout floats, zeroed here); a second small kernel applies noise / bias / activation and
+ * writes bf16 y.  agr_conv2d_tc_splits returns the split count this library would choose (1 = use the plain call). */
+int agr_conv2d_tc_splits(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);
+int agr_conv2d_tc_forward_splitk(const void* x, const void* w_krsc, void* y, float* workspace, int32_t splits, int32_t N,
+                                 int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, const float* bias,
+                                 const float* noise, const float* noise_w, int32_t activate, void* cuda_stream);
 /* Same kernel contracting x (N,H,W,Cin) with the input-channel SLICE [w_cin_offset, w_cin_offset+Cin) of a wider weight
  * (Cout,k,k,w_cin_total) and adding `residual` (H,W,Cout) fp32 (shared by the N images) before bias / activation;
  * out_fp32 != 0 stores the raw fp32 accumulator in y (N,H,W,Cout fp32) — the partial sum the second half consumes:
