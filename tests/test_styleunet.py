@@ -447,3 +447,25 @@ def test_grouped_equal_linear_equals_per_layer(built_lib):
         if gb is not None:
             assert torch.equal(gb, m.bias.grad)
     _cmp(lat.grad, lat2.grad, 1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,act,noise", [(1, 16, 16, 512, 512, 3, True, True), (1, 32, 64, 512, 256, 3, True, False),
+                                                      (2, 8, 16, 128, 64, 3, False, False), (1, 64, 64, 512, 512, 3, True, True)])
+def test_tcgen05_conv_split_k_equals_single_pass(N, H, W, Cin, Cout, k, act, noise, built_lib):
+    """agr_conv2d_tc_forward_splitk (slices of the (tap, channel-block) loop on different CTAs, fp32 atomics into a
+    workspace, finish kernel) against the single-pass kernel on the same operands: same fp32 products, different
+    summation order -> equal up to the final bf16 rounding."""
+    from animatablegaussians_b200 import _lib, styleunet_ops as ops
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    nz = torch.randn(1, 1, H, W, device="cuda", generator=g) if noise else None
+    nw = torch.tensor([0.5], device="cuda") if noise else None
+    splits = lib.agr_conv2d_tc_splits(N, H, W, Cin, Cout, k)
+    assert splits > 1
+    y1 = ops._tc_conv(x, w, Cout, k, b, nz, nw, act)
+    y2 = ops._tc_conv(x, w, Cout, k, b, nz, nw, act, splits=splits)
+    _cmp(y2, y1, 8e-3)
