@@ -22,9 +22,17 @@ _lib.register_symbols({
 })
 
 
+def cosine_lr(lr_init, iter_idx, iter_num, alpha=0.05):
+    """The trainer's schedule (main_avatar.py:61-68): cosine from lr_init down to alpha * lr_init over iter_num."""
+    import math
+    progress = iter_idx / iter_num
+    return lr_init * ((math.cos(math.pi * progress) + 1.0) * 0.5 * (1 - alpha) + alpha)
+
+
 class FlatAdam:
     def __init__(self, params, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
-        self.params = [p for p in params if p.requires_grad]
+        self._all_params = list(params)           # positions = torch.optim.Adam's parameter indices (checkpoints)
+        self.params = [p for p in self._all_params if p.requires_grad]
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
         # pad each tensor to a multiple of 4 elements so every view is 16-byte aligned
@@ -45,8 +53,71 @@ class FlatAdam:
             self._grad_views.append(self._flat_grad[o:o + k].view_as(p.data))
             p.grad = None
         self._bucket_clean = True   # bucket is all-zero: gathered gradients can be copied instead of added
-        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        # one group, torch.optim layout: the trainer's update_lr() writes param_groups[0]['lr'] (main_avatar.py:61-68)
+        self.param_groups = [dict(params=self._all_params, lr=lr, betas=tuple(betas), eps=eps, weight_decay=0, amsgrad=False)]
+        self._offsets = offs
+        self.t = 0
         self.device_step = torch.zeros(1, dtype=torch.int32, device=dev)  # used by step(graph_safe=True)
+
+    # lr / betas / eps live in param_groups[0] like torch.optim.Adam's.  NOTE: a CUDA graph captured around
+    # step(graph_safe=True) holds the learning rate of capture time as a kernel argument; re-capture to change it.
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, v):
+        self.param_groups[0]["lr"] = v
+
+    @property
+    def betas(self):
+        return self.param_groups[0]["betas"]
+
+    @property
+    def eps(self):
+        return self.param_groups[0]["eps"]
+
+    def state_dict(self):
+        """torch.optim.Adam's checkpoint layout (what the trainer stores in optm.pt, main_avatar.py:790-795): per-parameter
+        'step' / 'exp_avg' / 'exp_avg_sq' keyed by the parameter's index in the list given to the constructor."""
+        state = {}
+        t = max(self.t, int(self.device_step.item()))   # graph-safe steps count on the device
+        if t > 0:
+            index = {id(p): i for i, p in enumerate(self._all_params)}
+            for p, o in zip(self.params, self._offsets):
+                k = p.numel()
+                state[index[id(p)]] = {"step": torch.tensor(float(t)),
+                                       "exp_avg": self.exp_avg[o:o + k].view_as(p).clone(),
+                                       "exp_avg_sq": self.exp_avg_sq[o:o + k].view_as(p).clone()}
+        g = self.param_groups[0]
+        group = {"lr": g["lr"], "betas": tuple(g["betas"]), "eps": g["eps"], "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(self._all_params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """Accepts a torch.optim.Adam state_dict of the same parameter list (e.g. the authors' optm.pt) or our own."""
+        groups = sd["param_groups"]
+        n = sum(len(g["params"]) for g in groups)
+        if n != len(self._all_params):
+            raise ValueError("optimizer checkpoint holds %d parameters, this model has %d" % (n, len(self._all_params)))
+        g0 = groups[0]
+        self.param_groups[0].update(lr=g0["lr"], betas=tuple(g0["betas"]), eps=g0["eps"])
+        index = {id(p): i for i, p in enumerate(self._all_params)}
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+        t = 0
+        for p, o in zip(self.params, self._offsets):
+            st = sd["state"].get(index[id(p)])
+            if st is None:
+                continue
+            k = p.numel()
+            if st["exp_avg"].numel() != k:
+                raise ValueError("optimizer checkpoint: parameter %d has %d elements, expected %d" % (index[id(p)], st["exp_avg"].numel(), k))
+            self.exp_avg[o:o + k].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+            t = max(t, int(float(st["step"])))
+        self.t = t
+        self.device_step.fill_(t)
 
     def gather_grads(self):
         """Move the gradients autograd left in `p.grad` into the bucket (multi-tensor copy when the bucket is known to
