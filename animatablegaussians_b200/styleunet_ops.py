@@ -1,7 +1,8 @@
 """Operators of the B200 DualStyleUNet (see styleunet.py): autograd wrappers around the sm_100a kernels of
 include/agr_styleunet.h.  Activations are NHWC (torch channels_last), fp32 (parity tests) or bf16.
 
-Every operator has ONE implementation and no CPU / PyTorch fallback.  The dense contractions listed in
+No operator has a CPU / PyTorch fallback; the per-layer and the grouped (whole-net) forms of the weight preparation
+share their device code.  The dense contractions listed in
 LIBRARY_OPS are still vendor-library calls (cuDNN through torch) in this round and are reported as such by
 bench.py; everything around them (weight modulation/demodulation, noise + bias + activation, FIR resampling,
 Haar transforms) is hand-written CUDA.
@@ -22,9 +23,10 @@ import torch.nn.functional as F
 from . import _lib, stats
 
 LIBRARY_OPS = ("conv2d wgrad, all shapes (cuDNN via torch)",
-               "conv2d fwd/dgrad for stride-2, 8x8-resolution, Cin=3 and Cout in {12,32} layers (cuDNN via torch)",
+               "conv2d fwd/dgrad for stride-2 layers, 8x8 maps, and layers whose Cin or Cout is not a multiple of 64 "
+               "(3-channel inputs, 12-channel ToRGB, the 16/32-channel 1024^2 and 512^2 levels) (cuDNN / cuBLAS via torch)",
                "conv_transpose2d fwd/dgrad/wgrad (cuDNN via torch)",
-               "viewdir_net 4x4 convs (cuDNN via torch)", "style / modulation EqualLinear GEMVs (cuBLAS via torch)",
+               "viewdir_net 4x4 convs (cuDNN via torch)", "the 2-layer style MLP (cuBLAS via torch)",
                "CUB DeviceScan + DeviceRadixSort in the rasterizer binning (as in the reference)")
 
 _p = C.c_void_p
