@@ -1,0 +1,60 @@
+"""Photometric loss head after the rasterizer (first part): `photometric_loss` mirrors the
+L1 image + L1 mask terms of the trainer (main_avatar.py:193-222) for a batch of V views in ONE CUDA pass that also
+produces the gradients (include/agr_loss.h).  LPIPS and the patch crop are not part of it."""
+import ctypes as C
+
+import torch
+
+from . import _lib, stats
+
+_p = C.c_void_p
+_lib.register_symbols({
+    "agr_photometric_loss": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, C.c_float, C.c_float, _p, _p, _p, _p]),
+})
+
+
+class _PhotometricLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, alpha, gt_rgb, mask, boundary, bg, w_l1, w_mask):
+        lib = _lib.load()
+        rgb_c = rgb.detach().float().contiguous()
+        alpha_c = alpha.detach().float().contiguous() if alpha is not None else None
+        gt_c = gt_rgb.detach().float().contiguous()
+        m8, b8 = mask.to(torch.uint8).contiguous(), boundary.to(torch.uint8).contiguous()
+        bg_c = bg.detach().float().contiguous()
+        pixels = rgb_c.numel() // 3
+        if gt_c.numel() != 3 * pixels or m8.numel() != pixels or b8.numel() != pixels or (alpha_c is not None and alpha_c.numel() != pixels):
+            raise ValueError("photometric_loss: inconsistent shapes")
+        sums = torch.zeros(2, dtype=torch.float32, device=rgb_c.device)
+        d_rgb = torch.empty_like(rgb_c)
+        d_alpha = torch.empty_like(alpha_c) if alpha_c is not None else None
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        with torch.cuda.device(rgb_c.device), stats.stage("loss_head", launches=1):
+            st = lib.agr_photometric_loss(ptr(rgb_c), ptr(alpha_c), ptr(gt_c), ptr(m8), ptr(b8), ptr(bg_c), pixels, float(w_l1),
+                                          float(w_mask), ptr(sums), ptr(d_rgb), ptr(d_alpha),
+                                          C.c_void_p(torch.cuda.current_stream(rgb_c.device).cuda_stream))
+        if st != _lib.AGR_OK:
+            raise RuntimeError("agr_photometric_loss failed: %d" % st)
+        l1 = sums[0] / (3.0 * pixels)
+        mk = sums[1] / float(pixels)
+        ctx.save_for_backward(d_rgb, d_alpha)
+        ctx.shapes = (rgb.shape, None if alpha is None else alpha.shape)
+        ctx.mark_non_differentiable(l1, mk)
+        return w_l1 * l1 + w_mask * mk, l1, mk
+
+    @staticmethod
+    def backward(ctx, g_total, _g_l1, _g_mk):
+        d_rgb, d_alpha = ctx.saved_tensors
+        rs, as_ = ctx.shapes
+        gr = (d_rgb * g_total).view(rs) if ctx.needs_input_grad[0] else None
+        ga = (d_alpha * g_total).view(as_) if (d_alpha is not None and ctx.needs_input_grad[1]) else None
+        return gr, ga, None, None, None, None, None, None
+
+
+def photometric_loss(rgb_maps, mask_maps, color_imgs, mask_imgs, boundary_mask_imgs, bg_color, w_l1=1.0, w_mask=0.1):
+    """rgb_maps (V,H,W,3) / mask_maps (V,H,W,1) from `AvatarNet.render_views`, ground truth colour (V,H,W,3), boolean
+    masks (V,H,W), bg_color (3,) tensor.  Returns (w_l1 * l1 + w_mask * mask_loss, l1, mask_loss); the last two are
+    the per-term values the trainer logs (not differentiable)."""
+    if not rgb_maps.is_cuda:
+        raise RuntimeError("photometric_loss runs on the GPU only (no CPU fallback)")
+    return _PhotometricLoss.apply(rgb_maps, mask_maps, color_imgs, mask_imgs, boundary_mask_imgs, bg_color, w_l1, w_mask)

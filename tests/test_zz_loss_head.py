@@ -1,0 +1,48 @@
+"""Photometric loss head (first part).  CPU: the oracle against hand-computed values.  GPU: the
+fused kernel against the oracle — written after this round's GPU budget was spent, so its first hardware run is the
+round-end test pass: non-strict xfail until then (file sorts last so that nothing runs after it in the same process)."""
+import pytest
+import torch
+
+
+def test_loss_oracle_known_answer():
+    from oracle import loss_oracle as lo
+    H = W = 2
+    rgb = torch.tensor([[[0.2, 0.4, 0.6], [1.0, 1.0, 1.0]], [[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]]])
+    alpha = torch.tensor([[[0.9], [0.1]], [[0.5], [1.0]]])
+    gt = torch.tensor([[[0.1, 0.4, 0.9], [0.3, 0.3, 0.3]], [[0.2, 0.2, 0.2], [0.5, 0.7, 0.5]]])
+    mask = torch.tensor([[True, False], [True, True]])
+    boundary = torch.tensor([[False, False], [True, False]])
+    bg = torch.tensor([1.0, 1.0, 1.0])
+    l1, mk = lo.photometric_terms(rgb, alpha, gt, mask, boundary, bg)
+    # pixel (0,0): |0.1|+0+|0.3| = 0.4 ; (0,1): gt -> bg, img = 1 -> 0 ; (1,0): boundary -> both bg -> 0 ; (1,1): 0.2
+    assert abs(float(l1) - 0.6 / 12) < 1e-7
+    # mask: |0.9-1| + |0.1-0| + 0 (boundary) + |1-1| = 0.2 over 4 pixels
+    assert abs(float(mk) - 0.2 / 4) < 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after the r01 GPU budget was spent: first hardware run")
+@pytest.mark.parametrize("V,H,W", [(1, 64, 48), (3, 128, 160)])
+def test_photometric_loss_matches_oracle(V, H, W, built_lib):
+    from animatablegaussians_b200 import loss
+    from oracle import loss_oracle as lo
+    g = torch.Generator(device="cuda").manual_seed(21)
+    rgb = torch.rand(V, H, W, 3, device="cuda", generator=g).requires_grad_(True)
+    alpha = torch.rand(V, H, W, 1, device="cuda", generator=g).requires_grad_(True)
+    gt = torch.rand(V, H, W, 3, device="cuda", generator=g)
+    mask = torch.rand(V, H, W, device="cuda", generator=g) > 0.4
+    boundary = torch.rand(V, H, W, device="cuda", generator=g) > 0.9
+    bg = torch.tensor([1.0, 0.5, 0.25], device="cuda")
+    total, l1, mk = loss.photometric_loss(rgb, alpha, gt, mask, boundary, bg, w_l1=1.0, w_mask=0.1)
+    (2.0 * total).backward()
+    r2 = rgb.detach().double().cpu().requires_grad_(True)
+    a2 = alpha.detach().double().cpu().requires_grad_(True)
+    terms = [lo.photometric_terms(r2[v], a2[v], gt[v].double().cpu(), mask[v].cpu(), boundary[v].cpu(), bg.double().cpu()) for v in range(V)]
+    l1_ref = sum(t[0] for t in terms) / V
+    mk_ref = sum(t[1] for t in terms) / V
+    (2.0 * (l1_ref + 0.1 * mk_ref)).backward()
+    assert abs(float(l1) - float(l1_ref)) < 1e-5 and abs(float(mk) - float(mk_ref)) < 1e-5
+    assert abs(float(total) - float(l1_ref + 0.1 * mk_ref)) < 1e-5
+    assert torch.allclose(rgb.grad.double().cpu(), r2.grad, rtol=1e-5, atol=1e-10)
+    assert torch.allclose(alpha.grad.double().cpu(), a2.grad, rtol=1e-5, atol=1e-10)
