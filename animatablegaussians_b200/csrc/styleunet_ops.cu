@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) upfirdn_kernel(const T* __restrict__ x, T
 }
 
 // Blur (up = down = 1, K x K taps) on a channel-vectorisable tensor.  The one-pixel-per-thread kernel above issues K*K
-// vector loads + index arithmetic per output and is issue-bound (r01 ncu: ~1.1 TB/s at 16x1024x1024x16).  Here a
+// vector loads + index arithmetic per output and is issue-bound (r01 ncu: ~1.1 TB/s at 16x512x512x64).  Here a
 // thread owns ROWS vertically adjacent outputs of one channel vector and walks the ROWS+K-1 input rows once: each
 // loaded vector feeds up to K outputs ((ROWS+K-1)*K/ROWS = 7 loads per output for K = ROWS = 4 instead of 16).
 // Every output still accumulates its taps in (ky, kx) ascending order, so results are bit-identical to upfirdn_kernel.

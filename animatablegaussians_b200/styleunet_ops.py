@@ -24,7 +24,7 @@ from . import _lib, stats
 
 LIBRARY_OPS = ("conv2d wgrad, all shapes (cuDNN via torch)",
                "conv2d fwd/dgrad for stride-2 layers, 8x8 maps, and layers whose Cin or Cout is not a multiple of 64 "
-               "(3-channel inputs, 12-channel ToRGB, the 16/32-channel 1024^2 and 512^2 levels) (cuDNN / cuBLAS via torch)",
+               "(3-channel inputs, 12-channel ToRGB) (cuDNN / cuBLAS via torch)",
                "conv_transpose2d fwd/dgrad/wgrad (cuDNN via torch)",
                "viewdir_net 4x4 convs (cuDNN via torch)", "the 2-layer style MLP (cuBLAS via torch)",
                "CUB DeviceScan + DeviceRadixSort in the rasterizer binning (as in the reference)")
