@@ -33,8 +33,9 @@ def d_conv(x, w, *a, **kw):
 
 F.conv2d = timed("lib conv2d", d_conv, F.conv2d)
 F.conv_transpose2d = timed("lib conv_transpose2d", d_conv, F.conv_transpose2d)
-torch.nn.grad.conv2d_weight = timed("lib conv2d_weight", lambda x, ws, g, **kw: "x%s w%s g%s" % (tuple(x.shape), tuple(ws), tuple(g.shape)),
-                                    torch.nn.grad.conv2d_weight)
+torch.ops.aten.convolution_backward = timed(   # the explicit dgrad / wgrad calls of _ConvAct / _SplitConvAct
+    "lib convolution_backward", lambda dz, x, w, *a, **kw: "dz%s x%s w%s out_mask=%s" % (tuple(dz.shape), tuple(x.shape), tuple(w.shape), a[-1]),
+    torch.ops.aten.convolution_backward)
 ops._tc_conv = timed("tcgen05", lambda x, w, Cout, k, *a, **kw: "x%s Cout=%d k=%d" % (tuple(x.shape), Cout, k), ops._tc_conv)
 ops._tc_conv_split = timed("tcgen05 split", lambda x, w, Cout, k, *a, **kw: "x%s Cout=%d k=%d" % (tuple(x.shape), Cout, k), ops._tc_conv_split)
 
