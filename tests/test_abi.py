@@ -49,3 +49,30 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
         _lib.load()
+
+
+def test_ctypes_structs_match_the_c_headers(tmp_path):
+    """sizeof / offsetof of the by-value descriptor structs as gcc lays them out vs the ctypes mirrors (the host arrays
+    of agr_modweight_group_* / agr_equal_linear_group_* and the rasterizer argument blocks)."""
+    import subprocess
+    from animatablegaussians_b200 import _lib, styleunet_ops as ops
+    structs = {"AgrModWeightItem": (ops.AgrModWeightItem, "agr_styleunet.h"), "AgrEqualLinearItem": (ops.AgrEqualLinearItem, "agr_styleunet.h"),
+               "AgrRasterWorkspace": (_lib.AgrRasterWorkspace, "agr_rasterizer.h"), "AgrRasterForwardArgs": (_lib.AgrRasterForwardArgs, "agr_rasterizer.h"),
+               "AgrRasterBackwardArgs": (_lib.AgrRasterBackwardArgs, "agr_rasterizer.h")}
+    src = ['#include <stdio.h>', '#include <stddef.h>'] + sorted({'#include "%s"' % h for _, h in structs.values()}) + ["int main(void) {"]
+    for name, (cls, _) in structs.items():
+        src.append('printf("%s %%zu", sizeof(%s));' % (name, name))
+        for f, _t in cls._fields_:
+            src.append('printf(" %%zu", offsetof(%s, %s));' % (name, f))
+        src.append('printf("\\n");')
+    src.append("return 0; }")
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    for line in filter(None, out):
+        tok = line.split()
+        cls = structs[tok[0]][0]
+        assert int(tok[1]) == ctypes.sizeof(cls), tok[0]
+        assert [int(t) for t in tok[2:]] == [getattr(cls, f).offset for f, _ in cls._fields_], tok[0]
