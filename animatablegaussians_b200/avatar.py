@@ -265,13 +265,29 @@ class AvatarNet(nn.Module):
         half = viewdirs_map.shape[-1] // 2
         return torch.split(viewdirs_map, [half, half], -1)
 
+    def _viewdir_features(self, front, back):
+        """weight_viewdirs * viewdir_net(view map) for the front and the back maps (avatar.py:46-50,146-147):
+        Conv2d(1,64,4,2,1) -> LeakyReLU(0.2) -> Conv2d(64,128,4,2,1), both halves in one batch, on the kernels of
+        include/agr_conv.h (bias + activation in the epilogue) instead of two cuDNN convolutions each."""
+        c1, c2 = self.viewdir_net[0], self.viewdir_net[2]
+        dt = ops.compute_dtype()
+        Vn = front.shape[0]
+        x = torch.cat([front, back], 0).to(dt).contiguous(memory_format=torch.channels_last)   # (2V,1,h,w): C = 1
+        w1, h1 = ops.mod_weight(c1.weight, None, 1.0, False, dt)
+        w2, h2 = ops.mod_weight(c2.weight, None, 1.0, False, dt)
+        y = ops.conv2d(x, w1, h1, bias=c1.bias, activate=2, stride=2, pad=1)
+        y = ops.conv2d(y, w2, h2, bias=c2.bias, activate=0, stride=2, pad=1)
+        w = self.opt.get('weight_viewdirs', 1.)
+        if w != 1.:
+            y = y * w
+        return y[:Vn], y[Vn:]
+
     def get_viewdir_feat(self, items, live=None, cam_pos=None):
         with torch.no_grad():
             if live is None:
                 live = lbs.skin_points(self.lbs, items['cano2live_jnt_mats'], self.init_points, self.cano_nmls)
             front_viewdirs, back_viewdirs = self._viewdir_maps(items, *live, cam_pos=cam_pos)
-        w = self.opt.get('weight_viewdirs', 1.)
-        return w * self.viewdir_net(front_viewdirs), w * self.viewdir_net(back_viewdirs)
+        return self._viewdir_features(front_viewdirs, back_viewdirs)
 
     def get_viewdir_feat_batched(self, live, cam_pos):
         """get_viewdir_feat (avatar.py:126-147) for V camera centres at once -> two (V,128,S/8,S/8) features."""
@@ -289,8 +305,7 @@ class AvatarNet(nn.Module):
             vmap = F.interpolate(vmap.view(Vn, 1, Hm, Wm), None, 0.5, 'nearest')
             half = vmap.shape[-1] // 2
             front, back = torch.split(vmap, [half, half], -1)
-        w = self.opt.get('weight_viewdirs', 1.)
-        return w * self.viewdir_net(front), w * self.viewdir_net(back)
+        return self._viewdir_features(front, back)
 
     def get_pose_map(self, items):
         live_pts = lbs.skin_points(self.lbs, items['cano2live_jnt_mats_woRoot'], self.init_points)

@@ -1,151 +1,89 @@
-// Implicit-GEMM 3x3 / 1x1 convolution (stride 1, "same" padding) on the Blackwell tensor cores:
-// tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), operands staged in shared memory by TMA,
-// warp-specialised (1 TMA producer warp, 1 MMA issuer warp, 4 epilogue warps), mbarrier pipelines.
+// Implicit-GEMM convolutions on the Blackwell tensor cores (path 1 of include/agr_conv.h):
+// tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), operands staged in shared memory by TMA, warp-specialised
+// (1 TMA producer warp, 1 MMA issuer warp, 4 epilogue warps), mbarrier pipelines.
 //
 // Replaces the reference's dense contractions, which are cuDNN calls (conv2d_gradfix.py:34,66 via
-// dual_styleunet.py:114,275-296) followed by separate noise / bias / activation passes
-// (dual_styleunet.py:598-604): here noise injection + bias + leaky-ReLU(0.2)*sqrt(2) run in the epilogue,
-// straight out of TMEM.
+// dual_styleunet.py:114,275-296 and their autograd backward) followed by separate noise / bias / activation passes
+// (dual_styleunet.py:598-604): here noise injection + bias + leaky-ReLU run in the epilogue, straight out of TMEM.
 //
-// GEMM view (batch 1, NHWC bf16):  Y[p][co] = sum_{tap} sum_{ci} X[p + off(tap)][ci] * Wt[co][tap][ci]
-//   M = 128 output pixels = one 16 (w) x 8 (h) patch,   N = BN output channels,   K = taps * Cin in 64-blocks.
-// "im2col" never exists in memory: for each tap the A tile is ONE 3-D TMA box {64 ch, 16 w, 8 h} of the
-// activation, fetched at the tap's (dx, dy) shift; TMA zero-fills the out-of-image part (= the conv padding) and
-// writes the 128B-swizzled K-major layout tcgen05.mma reads directly.  B tiles are {64 ci, 1 tap, BN co} boxes of
-// the KRSC weight.  fp32 accumulators (128 lanes x BN columns) live in TMEM.
-#include <cuda.h>
-#include <cuda_bf16.h>
-#include <cuda_runtime.h>
-#include <cstdint>
-#include "../../include/agr_rasterizer.h"
-#include "../../include/agr_styleunet.h"
+// (1) conv_tc_kernel — forward form (forward of every layer, and every data gradient through the adjoint geometry):
+//   Y[g*os + phase][co] = sum_{tap} sum_{ci} X[g*is + off(tap)][ci] * Wt[co][tap][ci]
+//   M = 128 grid points = one 16 (w) x 8 (h) patch,   N = BN output channels,   K = taps * Cin in 64-blocks.
+//   "im2col" never exists in memory: for each tap the A tile is ONE TMA box {64 ch, 16 w, 8 h} of the activation fetched
+//   at the tap's shift — with element strides {1,2,2} for the stride-2 layers — TMA zero-fills the out-of-image part
+//   (= the conv padding) and writes the 128B-swizzled K-major layout tcgen05.mma reads directly.  B tiles are
+//   {64 ci, 1 tap, BN co} boxes of the KRSC weight.  A transposed convolution is stride^2 such sub-convolutions (one per
+//   output phase, blockIdx.z) that scatter to every stride-th output pixel: no zero insertion, no wasted MACs.
+//
+// (2) conv_wgrad_tc_kernel — weight gradient: dW[co][tap][ci] = sum_pixels X[p(tap)][ci] * dY[p][co], a GEMM with
+//   M = Cin, N = Cout, K = pixels.  NHWC tensors are channel-contiguous, i.e. MN-major for both operands: a TMA box
+//   {64 ch, 16 w, R h} with SWIZZLE_128B lands as 16R pixel rows of 128 B, the canonical UMMA MN-major SW128 layout with
+//   SBO = 1024 B (8-pixel groups) and LBO = the distance between consecutive 64-channel boxes.  A CTA owns a pixel
+//   slice x (Cin tile, Cout tile) x a GROUP of up to 3 taps that differ only by whole rows: the shifted operand is
+//   fetched once with R = 8 + halo rows and each tap's operand is the same box at a start address 16 pixels (2048 B,
+//   swizzle-phase preserving) further on.  fp32 tiles are RED-added into dW (split-K over pixels is inherent: K is up
+//   to 16 * 512^2), 128 B coalesced per instruction because TMEM lanes = consecutive ci.
+#include "conv_common.cuh"
 
 namespace agr {
 namespace tc {
 
-constexpr int TILE_W = 16, TILE_H = 8, BM = TILE_W * TILE_H;  // 128 pixels
+constexpr int TILE_W = 16, TILE_H = 8, BM = TILE_W * TILE_H;  // 128 grid points per tile
 constexpr int BK = 64;                                       // channels per k-block (128 B of bf16)
-// pipeline depth is a template parameter: 4 stages when the grid is a single wave (1 CTA/SM anyway), 3 stages (96 KB at
-// BN=128) when there are more tiles than SMs so that two CTAs per SM overlap one's epilogue with the other's mainloop
 constexpr int A_BYTES = BM * BK * 2;                         // 16 KB
 constexpr int NUM_THREADS = 192;                             // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "TCW_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra TCD_%=;\n\t"
-        "bra TCW_%=;\n\t"
-        "TCD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-//   [0,14) start >> 4, [16,30) LBO >> 4 (=1, unused for swizzled K-major), [32,46) SBO >> 4 (= 1024 B: 8 rows x 128 B),
-//   [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// Instruction descriptor (InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both,
-// N>>3 @17, M>>4 @24.
-__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
+constexpr int MAX_SMEM = 227 * 1024;
 
 struct ConvParams {
-    int N, H, W, Cin, Cout, taps, ksize;  // taps = ksize*ksize; N images share the weights
-    const float* bias;     // (Cout) or null
-    const float* noise;    // (H*W) or null
-    const float* noise_w;  // (1) or null
-    const float* residual;  // (H, W, Cout) fp32 added before bias/activation, shared by the N images; or null
-    float* y_f32;           // when set, the result is stored in fp32 here instead of bf16 in y (partial sums)
-    int w_cin_offset;      // first input channel of the weight slice this call contracts with (split-K over a concat)
-    int splits;            // > 1: blockIdx.z owns a contiguous slice of the (tap, channel-block) loop and ADDS its fp32
-                           // partial tile into y_f32 (zeroed by the caller); bias / noise / activation run in conv_finish_kernel
-    int activate;
-    __nv_bfloat16* y;      // (H, W, Cout)
+    int N, GH, GW;          // images, compute grid (output-phase coordinates)
+    int OH, OW;             // output tensor
+    int Cin, Cout;
+    int in_stride, out_stride;
+    TapList taps;
+    const float* bias;      // (Cout) or null
+    const float* noise;     // (OH*OW) or null
+    const float* noise_w;   // (1) or null
+    const float* residual;  // (OH, OW, Cout) fp32 added before bias/activation, shared by the N images; or null
+    float* y_f32;           // when set, the raw fp32 accumulator is stored here instead of bf16 in y
+    __nv_bfloat16* y;       // (N, OH, OW, Cout)
+    int w_cin_offset;       // first input channel of the weight slice this call contracts with (split contraction)
+    int activate;           // 0 | 1 lrelu*sqrt2 | 2 lrelu
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, (STAGES * (A_BYTES + BN * BK * 2) + 1024) * 2 <= 227 * 1024 ? 2 : 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, ConvParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, (STAGES * (A_BYTES + BN * BK * 2) + 1024) * 2 <= MAX_SMEM ? 2 : 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ ConvParams p) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_w = p.W / TILE_W;
-    const int tiles_img = tiles_w * (p.H / TILE_H);
+    const int tiles_w = (p.GW + TILE_W - 1) / TILE_W;
+    const int tiles_img = tiles_w * ((p.GH + TILE_H - 1) / TILE_H);
     const int img = blockIdx.x / tiles_img;
     const int tile_m = blockIdx.x - img * tiles_img;
     const int h0 = (tile_m / tiles_w) * TILE_H, w0 = (tile_m % tiles_w) * TILE_W;
     const int n0 = blockIdx.y * BN;
+    const int phase = blockIdx.z;
+    const int t_begin = p.taps.begin[phase];
     const int kchunks = p.Cin / BK;
-    const int num_kb_all = p.taps * kchunks;
-    const int kb0 = p.splits > 1 ? (int)(((long)blockIdx.z * num_kb_all) / p.splits) : 0;
-    const int kb1 = p.splits > 1 ? (int)(((long)(blockIdx.z + 1) * num_kb_all) / p.splits) : num_kb_all;
-    const int num_kb = kb1 - kb0;   // >= 1: the host keeps splits <= num_kb_all
-    const int pad = p.ksize / 2;
+    const int num_kb = (p.taps.begin[phase + 1] - t_begin) * kchunks;   // >= 1 (build_taps rejects empty phases)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
     }
-    if (warp == 1) {  // TMEM allocation: BN fp32 columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(BN) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_smem);   // BN fp32 columns (power of two >= 32)
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
@@ -155,28 +93,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                const int kb = kb0 + it;
-                const int tap = kb / kchunks, ck = kb - tap * kchunks;
-                const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+                const int tap = t_begin + it / kchunks, ck = it % kchunks;
                 unsigned char* a_dst = smem + s * STAGE_BYTES;
                 unsigned char* b_dst = a_dst + A_BYTES;
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_4d(a_dst, &map_x, &full_bar[s], ck * BK, w0 + dx, h0 + dy, img);   // OOB -> zeros = padding
-                tma_load_3d(b_dst, &map_w, &full_bar[s], p.w_cin_offset + ck * BK, tap, n0);
+                // OOB -> zeros = padding; with in_stride 2 the box holds every other pixel from its origin
+                tma_load_4d(a_dst, &map_x, &full_bar[s], ck * BK, p.in_stride * w0 + p.taps.dx[tap], p.in_stride * h0 + p.taps.dy[tap], img);
+                tma_load_3d(b_dst, &map_w, &full_bar[s], p.w_cin_offset + ck * BK, p.taps.wt[tap], n0);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one elected lane) =================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc(BM, BN);
+            const uint32_t idesc = umma_idesc(BM, BN, 0);
             for (int it = 0; it < num_kb; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t b_addr = a_addr + A_BYTES;
-                const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(b_addr);
+                const uint64_t adesc = umma_desc(a_addr, 16), bdesc = umma_desc(b_addr, 16);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 B -> +2 in the (>>4) start-address field
                     umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
@@ -185,24 +122,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             umma_commit(&tmem_full_bar);         // accumulator complete
         }
     } else {
-        // ================= epilogue: TMEM -> registers -> (+noise, +bias, lrelu) -> global =================
+        // ================= epilogue: TMEM -> registers -> (+residual, +noise, +bias, lrelu) -> global =================
         mbar_wait(&tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_fence_after();
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;             // pixel within the tile
-        const int h = h0 + row / TILE_W, w = w0 + row % TILE_W;
-        const size_t pix = (size_t)h * p.W + w;   // noise is per pixel, shared by the N images
-        const float add = (p.noise && p.noise_w) ? p.noise_w[0] * p.noise[pix] : 0.f;
-        __nv_bfloat16* out = p.y + ((size_t)img * p.H * p.W + pix) * p.Cout + n0;
+        const int row = q * 32 + lane;             // grid point within the tile
+        const int oy = (h0 + row / TILE_W) * p.out_stride + p.taps.py[phase];
+        const int ox = (w0 + row % TILE_W) * p.out_stride + p.taps.px[phase];
+        const bool valid = oy < p.OH && ox < p.OW;
+        const size_t pix = (size_t)oy * p.OW + ox;   // noise / residual are per output pixel, shared by the N images
+        const float add = (valid && p.noise && p.noise_w) ? p.noise_w[0] * p.noise[pix] : 0.f;
+        const size_t opix = (size_t)img * p.OH * p.OW + pix;
+        __nv_bfloat16* out = p.y + opix * p.Cout + n0;
         const float* res = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
-        float* out32 = p.y_f32 ? p.y_f32 + ((size_t)img * p.H * p.W + pix) * p.Cout + n0 : nullptr;
+        float* out32 = p.y_f32 ? p.y_f32 + opix * p.Cout + n0 : nullptr;
+        const float slope_gain = p.activate == 1 ? 1.4142135623730951f : 1.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            uint4 packed[4];
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(packed);
+            tmem_wait_ld();
+            if (!valid) continue;
             if (res) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -213,11 +153,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + rr.w);
                 }
             }
-            if (p.splits > 1) {   // split-K partial tile: accumulate into the zeroed fp32 workspace
-#pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(out32 + c0 + i, __uint_as_float(r[i]));
-                continue;
-            }
             if (out32) {   // fp32 partial result (no epilogue math): consumed as `residual` by the second half
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -225,13 +160,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                                                                            __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
                 continue;
             }
+            uint4 packed[4];
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(packed);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 float v0 = __uint_as_float(r[2 * i]) + add, v1 = __uint_as_float(r[2 * i + 1]) + add;
                 if (p.bias) { v0 += p.bias[n0 + c0 + 2 * i]; v1 += p.bias[n0 + c0 + 2 * i + 1]; }
                 if (p.activate) {
-                    v0 = (v0 > 0.f ? v0 : 0.2f * v0) * 1.4142135623730951f;
-                    v1 = (v1 > 0.f ? v1 : 0.2f * v1) * 1.4142135623730951f;
+                    v0 = (v0 > 0.f ? v0 : 0.2f * v0) * slope_gain;
+                    v1 = (v1 > 0.f ? v1 : 0.2f * v1) * slope_gain;
                 }
                 h2[i] = __floats2bfloat162_rn(v0, v1);
             }
@@ -239,60 +176,142 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i] = packed[i];
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 
-// ---- split-K finish: y = act(acc + noise_w * noise + bias) in bf16 from the fp32 accumulation buffer
-__global__ void __launch_bounds__(256) conv_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ y, long pixels,
-                                                         long pixels_per_image, int Cout, const float* __restrict__ bias,
-                                                         const float* __restrict__ noise, const float* __restrict__ noise_w,
-                                                         int activate) {
-    const int cv = Cout / 8;
-    const long total = pixels * cv;
-    const float nw = (noise && noise_w) ? noise_w[0] : 0.f;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % cv) * 8;
-        const long p = idx / cv;
-        const float add = noise ? nw * noise[p % pixels_per_image] : 0.f;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(acc + p * Cout + c));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(acc + p * Cout + c + 4));
-        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint4 packed;
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&packed);
+// ---- weight gradient ---------------------------------------------------------------------------------------------------
+struct WgradGroup {
+    int8_t dx, dy;        // origin shift of the shifted operand's box for this group
+    int8_t ntaps;         // 1..3 taps that share the box
+    int8_t r[3];          // row offset of each tap inside the box (units of 16-pixel rows)
+    int8_t wt[3];         // tap index in dW
+};
+
+struct WgradParams {
+    int N, GH, GW;          // pixel grid of the plain (unshifted) operand
+    int Cin, Cout, taps;    // taps = k*k
+    int stride;             // coordinate multiplier of the shifted operand's box origin (= its TMA element stride)
+    int x_shifted;          // 1: X is the shifted / strided operand (convolution); 0: dY is (transposed convolution)
+    int rows_x, rows_y;     // box heights (8, or 8 + halo for the shifted operand)
+    int slices, stages;
+    int ci_total, ci_offset;
+    int n_groups;
+    WgradGroup groups[16];
+    float* dw;              // (Cout, taps, ci_total) fp32, accumulated
+};
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ WgradParams p) {
+    constexpr int ROW_BYTES = TILE_W * BK * 2;               // 2048 B: 16 pixels x 64 channels
+    constexpr int MAX_STAGES = 4;
+    constexpr int TMEM_COLS = NT == 128 ? 512 : 256;        // 3 taps x NT fp32 columns, power of two
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_w = (p.GW + TILE_W - 1) / TILE_W, tiles_h = (p.GH + TILE_H - 1) / TILE_H;
+    const int boxes_img = tiles_w * tiles_h;
+    const long total_boxes = (long)p.N * boxes_img;
+    const int box0 = (int)((blockIdx.x * total_boxes) / p.slices), box1 = (int)(((blockIdx.x + 1) * total_boxes) / p.slices);
+    const int num_kb = box1 - box0;                        // host keeps slices <= total_boxes
+    const int n_tiles = p.Cout / NT;
+    const int ci0 = (blockIdx.y / n_tiles) * MT, co0 = (blockIdx.y % n_tiles) * NT;
+    const WgradGroup grp = p.groups[blockIdx.z];
+    const int a_box = p.rows_x * ROW_BYTES, b_box = p.rows_y * ROW_BYTES;     // one 64-channel box of each operand
+    const int a_bytes = (MT / 64) * a_box, stage_bytes = a_bytes + (NT / 64) * b_box;
+    const int STAGES = p.stages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_dy);
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int sx = p.x_shifted ? p.stride : 1, sy = p.x_shifted ? 1 : p.stride;
+            const int xdx = p.x_shifted ? grp.dx : 0, xdy = p.x_shifted ? grp.dy : 0;
+            const int ydx = p.x_shifted ? 0 : grp.dx, ydy = p.x_shifted ? 0 : grp.dy;
+            int s = 0; uint32_t ph = 0;
+            for (int it = 0; it < num_kb; ++it) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int b = box0 + it;
+                const int img = b / boxes_img, t = b - img * boxes_img;
+                const int h0 = (t / tiles_w) * TILE_H, w0 = (t % tiles_w) * TILE_W;
+                unsigned char* a_dst = smem + s * stage_bytes;
+                unsigned char* b_dst = a_dst + a_bytes;
+                mbar_expect_tx(&full_bar[s], stage_bytes);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float t = v[i] + add;
-            if (bias) t += bias[c + i];
-            if (activate) t = (t > 0.f ? t : 0.2f * t) * 1.4142135623730951f;
-            v[i] = t;
+                for (int j = 0; j < MT / 64; ++j) tma_load_4d(a_dst + j * a_box, &map_x, &full_bar[s], ci0 + 64 * j, sx * w0 + xdx, sx * h0 + xdy, img);
+#pragma unroll
+                for (int j = 0; j < NT / 64; ++j) tma_load_4d(b_dst + j * b_box, &map_dy, &full_bar[s], co0 + 64 * j, sy * w0 + ydx, sy * h0 + ydy, img);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
         }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(MT, NT, 1);   // a_major = b_major = MN
+            int s = 0; uint32_t ph = 0;
+            for (int it = 0; it < num_kb; ++it) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+                for (int t = 0; t < grp.ntaps; ++t) {
+                    const uint32_t a_t = a_addr + (p.x_shifted ? grp.r[t] * ROW_BYTES : 0);
+                    const uint32_t b_t = b_addr + (p.x_shifted ? 0 : grp.r[t] * ROW_BYTES);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) h2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        *reinterpret_cast<uint4*>(y + p * Cout + c) = packed;
-    }
-}
-
-// ---- KRSC weight -> the weight of the data-gradient convolution: out[ci][taps-1-t][co] = in[co][t][ci]
-__global__ void __launch_bounds__(256) weight_flip_transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                                   int Cout, int Cin, int taps) {
-    __shared__ __nv_bfloat16 tile[32][33];
-    const int t = blockIdx.z;
-    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    for (int r = ty; r < 32; r += 8) {
-        const int co = co0 + r, ci = ci0 + tx;
-        tile[r][tx] = (co < Cout && ci < Cin) ? in[((size_t)co * taps + t) * Cin + ci] : __float2bfloat16(0.f);
+                    for (int k = 0; k < BM / 16; ++k)   // 16 pixels per MMA = two 8-row groups = 2048 B
+                        umma_f16(tmem_base + t * NT, umma_desc(a_t + k * ROW_BYTES, a_box), umma_desc(b_t + k * ROW_BYTES, b_box), idesc,
+                                 (it | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        // accumulator row m (= input channel) sits in TMEM lane m for M = 128, lane (m % 16) + 32 * (m / 16) for M = 64
+        const int row = MT == 128 ? q * 32 + lane : q * 16 + lane;
+        const bool live = (MT == 128 || lane < 16) && num_kb > 0;
+        for (int t = 0; t < grp.ntaps; ++t) {
+            float* out = p.dw + ((size_t)co0 * p.taps + grp.wt[t]) * p.ci_total + p.ci_offset + ci0 + row;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NT; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NT + c0), r);
+                tmem_wait_ld();
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) atomicAdd(out + (size_t)(c0 + i) * p.taps * p.ci_total, __uint_as_float(r[i]));
+                }
+            }
+        }
+        tc_fence_before();
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int ci = ci0 + r, co = co0 + tx;
-        if (ci < Cin && co < Cout) out[((size_t)ci * taps + (taps - 1 - t)) * Cout + co] = tile[tx][r];
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 
@@ -312,19 +331,19 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static bool make_map_4d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t b0, uint32_t b1,
-                        uint32_t b2) {
+// NHWC activation (C, W, H, N): box of 64 channels x bw x bh pixels taken every `es`-th pixel (element strides)
+static bool make_map_act(CUtensorMap* m, const void* base, uint64_t C_, uint64_t W_, uint64_t H_, uint64_t N_, uint32_t bw, uint32_t bh, uint32_t es) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
-    cuuint64_t dims[4] = {d0, d1, d2, d3};
-    cuuint64_t strides[3] = {d0 * 2, d0 * d1 * 2, d0 * d1 * d2 * 2};
-    cuuint32_t box[4] = {b0, b1, b2, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint64_t dims[4] = {C_, W_, H_, N_};
+    cuuint64_t strides[3] = {C_ * 2, C_ * W_ * 2, C_ * W_ * H_ * 2};
+    cuuint32_t box[4] = {BK, bw * es, bh * es, 1};
+    cuuint32_t estr[4] = {1, es, es, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static bool make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2) {
+static bool make_map_w(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[3] = {d0, d1, d2};
@@ -343,106 +362,107 @@ static int launch_s(const CUtensorMap& mx, const CUtensorMap& mw, const ConvPara
         if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
         attr = true;
     }
-    dim3 grid(p.N * (p.H / TILE_H) * (p.W / TILE_W), p.Cout / BN, p.splits > 1 ? p.splits : 1);
+    dim3 grid(p.N * ((p.GH + TILE_H - 1) / TILE_H) * ((p.GW + TILE_W - 1) / TILE_W), p.Cout / BN, p.taps.n_phase);
     conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, s>>>(mx, mw, p);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 
-template <int BN>
-static int launch(const void* x, const void* w, const ConvParams& p, int w_cin_total, cudaStream_t s) {
+bool forward_supported(const AgrConvGeom& g) {
+    if (!geom_ok(g)) return false;
+    if (g.Cin % BK || g.Cout % 64) return false;
+    TapList t; int is, os, GH, GW;
+    return build_taps(g, &t, &is, &os, &GH, &GW);
+}
+
+int launch_forward(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, cudaStream_t s) {
+    ConvParams p;
+    if (!forward_supported(g) || !build_taps(g, &p.taps, &p.in_stride, &p.out_stride, &p.GH, &p.GW)) return AGR_ERR_INVALID_ARGUMENT;
+    const int cin_total = ep.w_cin_total > 0 ? ep.w_cin_total : g.Cin;
+    if (ep.w_cin_offset < 0 || (ep.w_cin_offset % BK) || ep.w_cin_offset + g.Cin > cin_total) return AGR_ERR_INVALID_ARGUMENT;
+    p.N = g.N; p.OH = g.OH; p.OW = g.OW; p.Cin = g.Cin; p.Cout = g.Cout;
+    p.bias = ep.out_fp32 ? nullptr : ep.bias; p.noise = ep.out_fp32 ? nullptr : ep.noise; p.noise_w = ep.out_fp32 ? nullptr : ep.noise_w;
+    p.residual = ep.residual; p.activate = ep.out_fp32 ? 0 : ep.activate; p.w_cin_offset = ep.w_cin_offset;
+    p.y = ep.out_fp32 ? nullptr : static_cast<__nv_bfloat16*>(y);
+    p.y_f32 = ep.out_fp32 ? static_cast<float*>(y) : nullptr;
     CUtensorMap mx, mw;
-    if (!make_map_4d(&mx, x, (uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N, BK, TILE_W, TILE_H)) return AGR_ERR_CUDA;
-    if (!make_map_3d(&mw, w, (uint64_t)w_cin_total, (uint64_t)p.taps, (uint64_t)p.Cout, BK, 1, BN)) return AGR_ERR_CUDA;
-    const long tiles = (long)p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN) * (p.splits > 1 ? p.splits : 1);
-    if (BN == 64 || tiles <= 148) return launch_s<BN, 4>(mx, mw, p, s);
-    return launch_s<BN, 3>(mx, mw, p, s);
+    if (!make_map_act(&mx, x, (uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N, TILE_W, TILE_H, (uint32_t)p.in_stride)) return AGR_ERR_CUDA;
+    const int BN = (g.Cout % 128 == 0) ? 128 : 64;
+    if (!make_map_w(&mw, w, (uint64_t)cin_total, (uint64_t)(g.ksize * g.ksize), (uint64_t)g.Cout, BK, 1, (uint32_t)BN)) return AGR_ERR_CUDA;
+    const long ctas = (long)p.N * ((p.GH + TILE_H - 1) / TILE_H) * ((p.GW + TILE_W - 1) / TILE_W) * (g.Cout / BN) * p.taps.n_phase;
+    // 4 stages when the grid is a single wave (1 CTA/SM anyway), 3 stages (96 KB at BN=128) otherwise so that two CTAs
+    // per SM overlap one's epilogue with the other's mainloop
+    if (BN == 64) return launch_s<64, 4>(mx, mw, p, s);
+    if (ctas <= 148) return launch_s<128, 4>(mx, mw, p, s);
+    return launch_s<128, 3>(mx, mw, p, s);
+}
+
+bool wgrad_supported(const AgrConvGeom& g) {
+    if (!geom_ok(g)) return false;
+    return g.Cin % 64 == 0 && g.Cout % 64 == 0;
+}
+
+template <int MT, int NT>
+static int launch_w(const CUtensorMap& mx, const CUtensorMap& mdy, const WgradParams& p, int smem, cudaStream_t s) {
+    static int attr = 0;
+    if (attr < smem) {
+        if (cudaFuncSetAttribute(conv_wgrad_tc_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
+        attr = smem;
+    }
+    dim3 grid((unsigned)p.slices, (unsigned)((p.Cin / MT) * (p.Cout / NT)), (unsigned)p.n_groups);
+    conv_wgrad_tc_kernel<MT, NT><<<grid, NUM_THREADS, smem, s>>>(mx, mdy, p);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int launch_wgrad(const AgrConvGeom& g, const void* x, const void* dy, float* dw, int ci_total, int ci_offset, cudaStream_t s) {
+    if (!wgrad_supported(g)) return AGR_ERR_INVALID_ARGUMENT;
+    WgradParams p;
+    const int k = g.ksize, st = g.stride;
+    p.N = g.N; p.Cin = g.Cin; p.Cout = g.Cout; p.taps = k * k; p.stride = st; p.dw = dw; p.ci_total = ci_total; p.ci_offset = ci_offset;
+    p.x_shifted = g.transposed ? 0 : 1;
+    // plain operand: dY for a convolution (grid = output), X for a transposed convolution (grid = input); in both the
+    // shifted operand is read at  stride * g + (k - pad)
+    p.GH = g.transposed ? g.H : g.OH; p.GW = g.transposed ? g.W : g.OW;
+    // groups: same kx, ky in one residue class mod stride -> rows (ky - ky_min) / stride apart, at most 3 per group
+    int ng = 0, halo = 0;
+    for (int kx = 0; kx < k; ++kx)
+        for (int c = 0; c < st; ++c) {
+            int n_in = 0;
+            for (int ky = c; ky < k; ky += st) {
+                if (n_in == 0) {
+                    if (ng >= 16) return AGR_ERR_INVALID_ARGUMENT;
+                    p.groups[ng].dx = (int8_t)(kx - g.pad); p.groups[ng].dy = (int8_t)(ky - g.pad); p.groups[ng].ntaps = 0;
+                }
+                WgradGroup& G = p.groups[ng];
+                G.r[G.ntaps] = (int8_t)n_in; G.wt[G.ntaps] = (int8_t)(ky * k + kx); ++G.ntaps;
+                if (n_in > halo) halo = n_in;
+                if (++n_in == 3) { ++ng; n_in = 0; }
+            }
+            if (n_in) ++ng;
+        }
+    p.n_groups = ng;
+    p.rows_x = TILE_H + (p.x_shifted ? halo : 0);
+    p.rows_y = TILE_H + (p.x_shifted ? 0 : halo);
+    const int MT = (g.Cin % 128 == 0) ? 128 : 64, NT = (g.Cout % 128 == 0) ? 128 : 64;
+    const int stage_bytes = ((MT / 64) * p.rows_x + (NT / 64) * p.rows_y) * TILE_W * BK * 2;
+    int stages = (MAX_SMEM - 1024) / stage_bytes;
+    if (stages > 4) stages = 4;
+    if (stages < 2) return AGR_ERR_INVALID_ARGUMENT;
+    p.stages = stages;
+    const long boxes = (long)g.N * ((p.GH + TILE_H - 1) / TILE_H) * ((p.GW + TILE_W - 1) / TILE_W);
+    const long tiles = (long)(g.Cin / MT) * (g.Cout / NT) * ng;
+    long slices = (2 * 148 + tiles - 1) / tiles;            // ~2 waves of CTAs (1 CTA / SM), each with >= 2 pixel boxes when possible
+    if (slices > boxes / 2) slices = boxes / 2;
+    if (slices < 1) slices = 1;
+    p.slices = (int)slices;
+    CUtensorMap mx, mdy;
+    if (!make_map_act(&mx, x, (uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N, TILE_W, (uint32_t)p.rows_x, p.x_shifted ? (uint32_t)st : 1u)) return AGR_ERR_CUDA;
+    if (!make_map_act(&mdy, dy, (uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N, TILE_W, (uint32_t)p.rows_y, p.x_shifted ? 1u : (uint32_t)st)) return AGR_ERR_CUDA;
+    const int smem = stages * stage_bytes + 1024;
+    if (MT == 128 && NT == 128) return launch_w<128, 128>(mx, mdy, p, smem, s);
+    if (MT == 128) return launch_w<128, 64>(mx, mdy, p, smem, s);
+    if (NT == 128) return launch_w<64, 128>(mx, mdy, p, smem, s);
+    return launch_w<64, 64>(mx, mdy, p, smem, s);
 }
 
 }  // namespace tc
 }  // namespace agr
-
-extern "C" {
-
-int agr_conv2d_tc_supported(int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize) {
-    using namespace agr::tc;
-    if (ksize != 1 && ksize != 3) return 0;
-    if (H < TILE_H || W < TILE_W || (H % TILE_H) || (W % TILE_W)) return 0;
-    if (Cin % BK) return 0;
-    if (Cout % 64) return 0;
-    return 1;
-}
-
-int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                          int32_t ksize, const float* bias, const float* noise, const float* noise_w, int32_t activate,
-                          void* cuda_stream) {
-    using namespace agr::tc;
-    if (!x || !w_krsc || !y || N < 1 || !agr_conv2d_tc_supported(H, W, Cin, Cout, ksize)) return AGR_ERR_INVALID_ARGUMENT;
-    ConvParams p;
-    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
-    p.bias = bias; p.noise = noise; p.noise_w = noise_w; p.activate = activate; p.y = static_cast<__nv_bfloat16*>(y);
-    p.residual = nullptr; p.y_f32 = nullptr; p.w_cin_offset = 0; p.splits = 1;
-    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-    if (Cout % 128 == 0) return launch<128>(x, w_krsc, p, Cin, s);
-    return launch<64>(x, w_krsc, p, Cin, s);
-}
-
-int agr_conv2d_tc_splits(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize) {
-    using namespace agr::tc;
-    if (!agr_conv2d_tc_supported(H, W, Cin, Cout, ksize)) return 1;
-    const int BN = (Cout % 128 == 0) ? 128 : 64;
-    const long tiles = (long)N * (H / TILE_H) * (W / TILE_W) * (Cout / BN);
-    const int num_kb = ksize * ksize * (Cin / BK);
-    // fill ~2 CTAs per SM, but keep >= 4 (tap, channel-block) steps per CTA so the pipeline still overlaps
-    long s = (2 * 148) / tiles;
-    if (s > num_kb / 4) s = num_kb / 4;
-    if (s > 32) s = 32;
-    return s < 2 ? 1 : (int)s;
-}
-
-int agr_conv2d_tc_forward_splitk(const void* x, const void* w_krsc, void* y, float* workspace, int32_t splits, int32_t N, int32_t H,
-                                 int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, const float* bias, const float* noise,
-                                 const float* noise_w, int32_t activate, void* cuda_stream) {
-    using namespace agr::tc;
-    if (!x || !w_krsc || !y || !workspace || N < 1 || !agr_conv2d_tc_supported(H, W, Cin, Cout, ksize)) return AGR_ERR_INVALID_ARGUMENT;
-    if (splits < 2 || splits > ksize * ksize * (Cin / BK)) return AGR_ERR_INVALID_ARGUMENT;
-    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-    const long pixels = (long)N * H * W;
-    if (cudaMemsetAsync(workspace, 0, (size_t)pixels * Cout * sizeof(float), s) != cudaSuccess) return AGR_ERR_CUDA;
-    ConvParams p;
-    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
-    p.bias = nullptr; p.noise = nullptr; p.noise_w = nullptr; p.activate = 0; p.y = nullptr;
-    p.residual = nullptr; p.y_f32 = workspace; p.w_cin_offset = 0; p.splits = splits;
-    const int st = (Cout % 128 == 0) ? launch<128>(x, w_krsc, p, Cin, s) : launch<64>(x, w_krsc, p, Cin, s);
-    if (st != AGR_OK) return st;
-    const long total = pixels * (Cout / 8);
-    long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
-    conv_finish_kernel<<<(unsigned)g, 256, 0, s>>>(workspace, static_cast<__nv_bfloat16*>(y), pixels, (long)H * W, Cout, bias, noise, noise_w, activate);
-    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
-}
-
-int agr_conv2d_tc_forward_split(const void* x, const void* w_krsc, void* y, int32_t out_fp32, int32_t N, int32_t H, int32_t W,
-                                int32_t Cin, int32_t Cout, int32_t ksize, int32_t w_cin_total, int32_t w_cin_offset,
-                                const float* residual, const float* bias, int32_t activate, void* cuda_stream) {
-    using namespace agr::tc;
-    if (!x || !w_krsc || !y || N < 1 || !agr_conv2d_tc_supported(H, W, Cin, Cout, ksize)) return AGR_ERR_INVALID_ARGUMENT;
-    if (w_cin_offset < 0 || (w_cin_offset % BK) || w_cin_offset + Cin > w_cin_total) return AGR_ERR_INVALID_ARGUMENT;
-    ConvParams p;
-    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.taps = ksize * ksize;
-    p.bias = bias; p.noise = nullptr; p.noise_w = nullptr; p.activate = activate;
-    p.y = out_fp32 ? nullptr : static_cast<__nv_bfloat16*>(y);
-    p.y_f32 = out_fp32 ? static_cast<float*>(y) : nullptr;
-    p.residual = residual; p.w_cin_offset = w_cin_offset; p.splits = 1;
-    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-    if (Cout % 128 == 0) return launch<128>(x, w_krsc, p, w_cin_total, s);
-    return launch<64>(x, w_krsc, p, w_cin_total, s);
-}
-
-int agr_weight_flip_transpose(const void* w_krsc, void* w_out, int32_t Cout, int32_t Cin, int32_t ksize, void* cuda_stream) {
-    if (!w_krsc || !w_out || Cout < 1 || Cin < 1 || ksize < 1) return AGR_ERR_INVALID_ARGUMENT;
-    dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, ksize * ksize);
-    agr::tc::weight_flip_transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
-        static_cast<const __nv_bfloat16*>(w_krsc), static_cast<__nv_bfloat16*>(w_out), Cout, Cin, ksize * ksize);
-    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
-}
-
-}  // extern "C"

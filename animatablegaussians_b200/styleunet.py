@@ -105,10 +105,8 @@ class EqualLinear(nn.Module):
         self.lr_mul = lr_mul
 
     def forward(self, x):
-        if self.activation:
-            b = self.bias * self.lr_mul if self.bias is not None else None
-            return ops.bias_act(nn.functional.linear(x, self.weight * self.scale), b)
-        return ops.equal_linear(x, self.weight, self.bias, self.scale, self.lr_mul)
+        y = ops.equal_linear(x, self.weight, self.bias, self.scale, self.lr_mul)
+        return ops.bias_act(y, None) if self.activation else y   # fused_leaky_relu(x W^T * scale, bias * lr_mul)
 
 
 class EqualConv2d(nn.Module):
@@ -367,7 +365,7 @@ class DualStyleUNet(nn.Module):
 
         def plain(layer):   # ConvLayer: [Blur,] EqualConv2d [, FusedLeakyReLU]
             conv = layer[1] if layer.has_blur else layer[0]
-            entries.append((conv.weight, None, conv.scale, False, False))
+            entries.append((conv.weight, None, conv.scale, False))
 
         plain(self.conv_in)
         for from_rgb, cond_conv in zip(self.from_rgbs, self.cond_convs):
@@ -383,7 +381,7 @@ class DualStyleUNet(nn.Module):
         else:
             styles = [c.modulation(latent[:, i]) for c, i in mods]
         for (c, _), s in zip(mods, styles):
-            entries.append((c.weight, s, c.scale, c.demodulate, c.upsample))
+            entries.append((c.weight, s, c.scale, c.demodulate))
         return ops.prepare_weights(entries, ops.compute_dtype())
 
     # ------------------------------------------------------------------ reference-shaped forward

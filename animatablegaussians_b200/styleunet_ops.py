@@ -2,10 +2,9 @@
 include/agr_styleunet.h.  Activations are NHWC (torch channels_last), fp32 (parity tests) or bf16.
 
 No operator has a CPU / PyTorch fallback; the per-layer and the grouped (whole-net) forms of the weight preparation
-share their device code.  The dense contractions listed in
-LIBRARY_OPS are still vendor-library calls (cuDNN through torch) in this round and are reported as such by
-bench.py; everything around them (weight modulation/demodulation, noise + bias + activation, FIR resampling,
-Haar transforms) is hand-written CUDA.
+share their device code.  Every dense contraction (convolutions and transposed convolutions, forward / data gradient /
+weight gradient: include/agr_conv.h) and everything around them (weight modulation/demodulation, noise + bias +
+activation, FIR resampling, Haar transforms) is hand-written CUDA; no cuDNN / cuBLAS call remains on the path.
 
 Semantics restated from the reference:
   bias_act            network/styleunet/fused_act.py:100-132, fused_bias_act_kernel.cu:18-65 (act=3)
@@ -22,12 +21,8 @@ import torch.nn.functional as F
 
 from . import _lib, stats
 
-LIBRARY_OPS = ("conv2d wgrad, all shapes (cuDNN via torch)",
-               "conv2d fwd/dgrad for stride-2 layers, 8x8 maps, and layers whose Cin or Cout is not a multiple of 64 "
-               "(3-channel inputs, 12-channel ToRGB) (cuDNN / cuBLAS via torch)",
-               "conv_transpose2d fwd/dgrad/wgrad (cuDNN via torch)",
-               "viewdir_net 4x4 convs (cuDNN via torch)", "the 2-layer style MLP (cuBLAS via torch)",
-               "CUB DeviceScan + DeviceRadixSort in the rasterizer binning (as in the reference)")
+# what is still a vendor-library call on the StyleUNet / avatar path (reported by bench.py): no convolution, no GEMM
+LIBRARY_OPS = ("CUB DeviceScan + DeviceRadixSort in the rasterizer binning (as in the reference)",)
 
 _p = C.c_void_p
 class AgrModWeightItem(C.Structure):
@@ -54,15 +49,9 @@ _lib.register_symbols({
     "agr_bias_act_backward": (C.c_int, [C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, _p, C.c_int64, _p, _p, C.c_int32, _p]),
     "agr_modweight_forward": (C.c_int, [C.c_int32, _p, _p, C.c_float] + [C.c_int32] * 5 + [_p, _p, _p]),
     "agr_modweight_backward": (C.c_int, [C.c_int32, _p, _p, C.c_float] + [C.c_int32] * 5 + [_p, _p, _p, _p, _p]),
-    "agr_conv2d_tc_supported": (C.c_int, [C.c_int32] * 5),
-    "agr_conv2d_tc_forward": (C.c_int, [_p, _p, _p] + [C.c_int32] * 6 + [_p, _p, _p, C.c_int32, _p]),
-    "agr_conv2d_tc_splits": (C.c_int, [C.c_int32] * 6),
-    "agr_conv2d_tc_forward_splitk": (C.c_int, [_p, _p, _p, _p] + [C.c_int32] * 7 + [_p, _p, _p, C.c_int32, _p]),
-    "agr_weight_flip_transpose": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
     "agr_sum_batch": (C.c_int, [C.c_int32, _p, _p, C.c_int32, C.c_int64, _p]),
     "agr_bilinear2x_add_forward": (C.c_int, [C.c_int32, _p, _p, _p] + [C.c_int32] * 5 + [_p]),
     "agr_bilinear2x_backward": (C.c_int, [C.c_int32, _p, _p] + [C.c_int32] * 4 + [_p]),
-    "agr_conv2d_tc_forward_split": (C.c_int, [_p, _p, _p] + [C.c_int32] * 9 + [_p, _p, C.c_int32, _p]),
     "agr_wavelet_upsample": (C.c_int, [C.c_int32, C.c_int32, _p, _p] + [C.c_int32] * 4 + [C.POINTER(C.c_float), _p]),
     "agr_equal_linear_forward": (C.c_int, [_p, _p, _p, C.c_float, C.c_float, C.c_int32, C.c_int32, _p, _p]),
     "agr_equal_linear_backward": (C.c_int, [_p, _p, _p, C.c_float, C.c_float, C.c_int32, C.c_int32, _p, _p, _p, _p]),
@@ -483,10 +472,11 @@ def bilinear_resize(x, size):
 # ------------------------------------------------------------------------------------------ weight preparation
 class _ModWeight(torch.autograd.Function):
     """(Cout,Cin,k,k) fp32 master weight + (Cin,) style -> conv-ready weight in the compute dtype, KRSC memory
-    (torch channels_last).  transpose_io -> (Cin,Cout,k,k) operand of conv_transpose2d."""
+    (torch channels_last), appended to `sink`; the autograd output is its fp32 gradient HANDLE (see _ModWeightGroup).
+    transpose_io -> (Cin,Cout,k,k) layout."""
 
     @staticmethod
-    def forward(ctx, weight, s, scale, demodulate, transpose_io, dtype):
+    def forward(ctx, weight, s, scale, demodulate, transpose_io, dtype, sink):
         lib = _lib.load()
         w = weight.detach().float().contiguous()
         Cout, Cin, k = w.shape[-4], w.shape[-3], w.shape[-1]
@@ -497,9 +487,10 @@ class _ModWeight(torch.autograd.Function):
         with torch.cuda.device(w.device), stats.stage("styleunet_weight", launches=1):
             _check(lib.agr_modweight_forward(_code(out), _ptr(w), _ptr(sv), float(scale), Cout, Cin, k, int(demodulate),
                                              int(transpose_io), _ptr(out), _ptr(demod), _stream(w)), "agr_modweight_forward")
+        sink.append(out)
         ctx.save_for_backward(w, sv, demod)
         ctx.meta = (float(scale), Cout, Cin, k, demodulate, transpose_io, weight.shape, s.shape)
-        return out
+        return _zero_scalar(w.device).expand(shape)
 
     @staticmethod
     def backward(ctx, g):
@@ -512,7 +503,16 @@ class _ModWeight(torch.autograd.Function):
         with torch.cuda.device(w.device), stats.stage("styleunet_weight", launches=1):
             _check(lib.agr_modweight_backward(_code(g), _ptr(w), _ptr(sv), scale, Cout, Cin, k, int(demodulate), int(transpose_io),
                                               _ptr(g), _ptr(demod), _ptr(dw), _ptr(ds), _stream(w)), "agr_modweight_backward")
-        return dw.view(wshape), ds.view(sshape), None, None, None, None
+        return dw.view(wshape), ds.view(sshape), None, None, None, None, None
+
+
+def mod_weight(weight, s, scale, demodulate, dtype, transpose_io=False):
+    """-> (conv-ready operand, fp32 gradient handle) of one layer (per-layer form of prepare_weights)."""
+    if s is None:
+        s = _ones(weight.shape[-3], weight.device)
+    sink = []
+    handle = _ModWeight.apply(weight, s, scale, demodulate, transpose_io, dtype, sink)
+    return sink[0], handle
 
 
 def _addr(t):
@@ -521,16 +521,22 @@ def _addr(t):
 
 class _ModWeightGroup(torch.autograd.Function):
     """_ModWeight for every conv layer of a U-Net at once (agr_modweight_group_*): `specs[l] = (scale, demodulate,
-    transpose_io)`, `tensors = (weight_0, s_0, weight_1, s_1, ...)` with s_l = None for a plain equalised conv."""
+    transpose_io)`, `tensors = (weight_0, s_0, weight_1, s_1, ...)` with s_l = None for a plain equalised conv.
+
+    The conv-ready operands (compute dtype) are appended to `sink`; the autograd outputs are fp32 HANDLES of the
+    operands' logical shape (stride-0 views of one zero: no memory, never read).  The convolutions return their fp32
+    weight gradients against the handle, so dW reaches the modulation backward in fp32 without a cast through the
+    operand's bf16 dtype (autograd would otherwise cast every gradient to the dtype of the forward output)."""
 
     @staticmethod
-    def forward(ctx, specs, dtype, *tensors):
+    def forward(ctx, specs, dtype, sink, *tensors):
         lib = _lib.load()
         L = len(specs)
         ws = [tensors[2 * l].detach().float().contiguous() for l in range(L)]
         dev = ws[0].device
-        svs, outs, demods = [], [], []
+        svs, outs, demods, handles = [], [], [], []
         items = (AgrModWeightItem * L)()
+        zero = _zero_scalar(dev)
         for l, (scale, demodulate, transpose_io) in enumerate(specs):
             w, s = ws[l], tensors[2 * l + 1]
             Cout, Cin, k = w.shape[-4], w.shape[-3], w.shape[-1]
@@ -538,28 +544,29 @@ class _ModWeightGroup(torch.autograd.Function):
             shape = (Cin, Cout, k, k) if transpose_io else (Cout, Cin, k, k)
             out = torch.empty(shape, dtype=dtype, device=dev, memory_format=_CL)
             demod = torch.empty(Cout, dtype=torch.float32, device=dev) if demodulate else None
-            svs.append(sv); outs.append(out); demods.append(demod)
+            svs.append(sv); outs.append(out); demods.append(demod); handles.append(zero.expand(shape))
             it = items[l]
             it.w, it.s, it.w_out, it.demod = w.data_ptr(), sv.data_ptr(), out.data_ptr(), _addr(demod)
             it.scale, it.Cout, it.Cin, it.k = float(scale), Cout, Cin, k
             it.demodulate, it.transpose_io = int(bool(demodulate)), int(bool(transpose_io))
         with torch.cuda.device(dev), stats.stage("styleunet_weight", launches=(L + 39) // 40):
             _check(lib.agr_modweight_group_forward(_code(outs[0]), items, L, _stream(ws[0])), "agr_modweight_group_forward")
+        sink.extend(outs)
         ctx.save_for_backward(*ws, *svs, *[d for d in demods if d is not None])
         ctx.meta = (specs, [d is not None for d in demods], [tensors[2 * l].shape for l in range(L)],
-                    [None if tensors[2 * l + 1] is None else tensors[2 * l + 1].shape for l in range(L)], dtype)
-        return tuple(outs)
+                    [None if tensors[2 * l + 1] is None else tensors[2 * l + 1].shape for l in range(L)])
+        return tuple(handles)
 
     @staticmethod
     def backward(ctx, *gs):
         lib = _lib.load()
-        specs, has_demod, wshapes, sshapes, dtype = ctx.meta
+        specs, has_demod, wshapes, sshapes = ctx.meta
         L = len(specs)
         saved = ctx.saved_tensors
         ws, svs, rest = saved[:L], saved[L:2 * L], list(saved[2 * L:])
         dev = ws[0].device
         items = (AgrModWeightItem * L)()
-        keep, grads = [], [None, None]
+        keep, grads = [], [None, None, None]
         for l, (scale, demodulate, transpose_io) in enumerate(specs):
             w = ws[l]
             Cout, Cin, k = w.shape[-4], w.shape[-3], w.shape[-1]
@@ -567,10 +574,10 @@ class _ModWeightGroup(torch.autograd.Function):
             g = gs[l]
             if g is None:   # a layer this forward never used
                 shape = (Cin, Cout, k, k) if transpose_io else (Cout, Cin, k, k)
-                g = torch.zeros(shape, dtype=dtype, device=dev)
-            g = g.contiguous(memory_format=_CL)
+                g = torch.zeros(shape, dtype=torch.float32, device=dev)
+            g = g.float().contiguous(memory_format=_CL)
             dw = torch.empty_like(w)
-            ds = _zeros(Cin, dev) if sshapes[l] is not None and ctx.needs_input_grad[3 + 2 * l] else None
+            ds = _zeros(Cin, dev) if sshapes[l] is not None and ctx.needs_input_grad[4 + 2 * l] else None
             keep.append((g, dw, ds))
             it = items[l]
             it.w, it.s, it.demod, it.d_wout = w.data_ptr(), svs[l].data_ptr(), _addr(demod), g.data_ptr()
@@ -579,12 +586,19 @@ class _ModWeightGroup(torch.autograd.Function):
             it.demodulate, it.transpose_io = int(bool(demodulate)), int(bool(transpose_io))
             grads.append(dw.view(wshapes[l]))
             grads.append(ds.view(sshapes[l]) if ds is not None else None)
-        code = _code(keep[0][0])
-        if any(_code(k_[0]) != code for k_ in keep):
-            raise RuntimeError("modweight group: mixed gradient dtypes")
         with torch.cuda.device(dev), stats.stage("styleunet_weight", launches=(L + 39) // 40):
-            _check(lib.agr_modweight_group_backward(code, items, L, _stream(ws[0])), "agr_modweight_group_backward")
+            _check(lib.agr_modweight_group_backward(0, items, L, _stream(ws[0])), "agr_modweight_group_backward")
         return tuple(grads)
+
+
+_zero_cache = {}
+
+
+def _zero_scalar(dev):
+    key = str(dev)
+    if key not in _zero_cache:
+        _zero_cache[key] = torch.zeros(1, dtype=torch.float32, device=dev)
+    return _zero_cache[key]
 
 
 # A "weight plan" holds the conv-ready operands of every layer of one U-Net for one step, prepared by the grouped
@@ -603,32 +617,25 @@ def weight_plan(plan):
 
 
 def planned_weight(weight, dtype):
+    """-> (operand, gradient handle) of this parameter in the active weight plan, or None."""
     if _plan is None:
         return None
-    w = _plan.get(id(weight))
-    return w if w is not None and w.dtype == dtype else None
+    hit = _plan.get(id(weight))
+    return hit if hit is not None and hit[0].dtype == dtype else None
 
 
 def prepare_weights(entries, dtype):
-    """entries: [(weight parameter, style modulation s (1,Cin) or None, scale, demodulate, transpose_io)] ->
-    {id(weight): prepared operand}."""
+    """entries: [(weight parameter, style modulation s (1,Cin) or None, scale, demodulate)] ->
+    {id(weight): (conv-ready KRSC operand in `dtype`, fp32 gradient handle)}."""
     if not entries:
         return {}
-    specs = tuple((float(e[2]), bool(e[3]), bool(e[4])) for e in entries)
+    specs = tuple((float(e[2]), bool(e[3]), False) for e in entries)
     flat = []
     for e in entries:
         flat += [e[0], e[1]]
-    outs = _ModWeightGroup.apply(specs, dtype, *flat)
-    return {id(e[0]): o for e, o in zip(entries, outs)}
-
-
-def _prepared(weight, s, scale, demodulate, transpose_io, dtype):
-    w = planned_weight(weight, dtype)
-    if w is not None:
-        return w
-    if s is None:
-        s = _ones(weight.shape[-3], weight.device)
-    return _ModWeight.apply(weight, s, scale, demodulate, transpose_io, dtype)
+    sink = []
+    handles = _ModWeightGroup.apply(specs, dtype, sink, *flat)
+    return {id(e[0]): (o, h) for e, o, h in zip(entries, sink, handles)}
 
 
 class _EqualLinearVec(torch.autograd.Function):
@@ -754,95 +761,162 @@ def _ones(n, dev):
 
 
 # ------------------------------------------------------------------------------------------ dense contractions
-def _tc_ok(x, Cout, k, stride):
-    if x.dtype != torch.bfloat16 or stride != 1:
-        return False
-    return bool(_lib.load().agr_conv2d_tc_supported(x.shape[2], x.shape[3], x.shape[1], Cout, k))
+class AgrConvGeom(C.Structure):
+    """include/agr_conv.h"""
+    _fields_ = [(n, C.c_int32) for n in ("N", "H", "W", "Cin", "OH", "OW", "Cout", "ksize", "stride", "pad", "transposed")]
 
 
-def _tc_conv(x, w, Cout, k, bias, noise, noise_w, activate, splits=1):
-    """x (N,Cin,H,W) NHWC bf16, w (Cout,Cin,k,k) KRSC bf16 -> (N,Cout,H,W) NHWC bf16 on tcgen05.
-    `splits > 1` selects the split-K form (agr_conv2d_tc_forward_splitk).  The step does not use it: measured inside the
-    whole-step graph (r01, profiles/SUMMARY_r01.md) the memset + finish launches and the fp32 atomics cost more than the
-    idle SMs of the coarse levels give back (310.6 vs 317.3 views/s); it stays covered by tests/test_styleunet.py."""
+class AgrConvEpilogue(C.Structure):
+    """include/agr_conv.h"""
+    _fields_ = [("bias", _p), ("noise", _p), ("noise_w", _p), ("residual", _p), ("activate", C.c_int32), ("out_fp32", C.c_int32),
+                ("w_cin_total", C.c_int32), ("w_cin_offset", C.c_int32)]
+
+
+_lib.register_symbols({
+    "agr_conv2d_path": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), C.c_int32]),
+    "agr_conv2d_forward": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), _p, _p, _p, C.POINTER(AgrConvEpilogue), _p]),
+    "agr_conv2d_dgrad": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), _p, _p, _p, _p]),
+    "agr_conv2d_wgrad": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), _p, _p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
+    "agr_weight_transpose": (C.c_int, [C.c_int32, _p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
+})
+
+_STAGE = {1: "styleunet_conv_tc", 2: "styleunet_conv_direct"}
+
+
+def conv_geom(x_shape, Cout, k, stride=1, pad=None, transposed=False):
+    """Geometry of one layer (include/agr_conv.h): x_shape = (N, Cin, H, W), the logical NCHW shape of the input."""
+    N, Cin, H, W = (int(v) for v in x_shape)
+    pad = k // 2 if pad is None else int(pad)
+    if transposed:
+        OH, OW = (H - 1) * stride - 2 * pad + k, (W - 1) * stride - 2 * pad + k
+    else:
+        OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    return AgrConvGeom(N, H, W, Cin, OH, OW, int(Cout), int(k), int(stride), pad, int(bool(transposed)))
+
+
+def _flops(g):
+    pix = g.N * (g.H * g.W if g.transposed else g.OH * g.OW)
+    return 2.0 * pix * g.Cin * g.Cout * g.ksize * g.ksize
+
+
+def conv_path(x, g, what=0):
+    """1 = tcgen05, 2 = CUDA-core direct (agr_conv2d_path); what: 0 forward, 1 data gradient, 2 weight gradient."""
+    return int(_lib.load().agr_conv2d_path(_code(x), C.byref(g), what))
+
+
+def conv_forward(x, w, g, bias=None, noise=None, noise_w=None, activate=0, residual=None, out_fp32=False, cin_total=0, cin_offset=0):
+    """x (N,Cin,H,W) NHWC, w KRSC (Cout, cin_total or Cin, k, k) channels_last -> y (N,Cout,OH,OW) NHWC."""
     lib = _lib.load()
-    y = _new_like(x, Cout, x.shape[2], x.shape[3])
-    stats.add_work("styleunet_conv_tc", 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * x.shape[1] * Cout * k * k)
-    N, Cin, H, W = x.shape
-    if splits > 1:   # a handful of output tiles, long contraction -> split-K over the idle SMs
-        ws = torch.empty(N * H * W * Cout, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=2):
-            _check(lib.agr_conv2d_tc_forward_splitk(_ptr(x), _ptr(w), _ptr(y), _ptr(ws), splits, N, H, W, Cin, Cout, k, _ptr(bias),
-                                                    _ptr(noise), _ptr(noise_w), int(activate), _stream(x)), "agr_conv2d_tc_forward_splitk")
-        return y
-    with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=1):
-        _check(lib.agr_conv2d_tc_forward(_ptr(x), _ptr(w), _ptr(y), N, H, W, Cin, Cout, k, _ptr(bias),
-                                         _ptr(noise), _ptr(noise_w), int(activate), _stream(x)), "agr_conv2d_tc_forward")
+    y = torch.empty((g.N, g.Cout, g.OH, g.OW), dtype=torch.float32 if out_fp32 else x.dtype, device=x.device, memory_format=_CL)
+    ep = AgrConvEpilogue(_addr(bias), _addr(noise), _addr(noise_w if noise is not None else None), _addr(residual), int(activate),
+                         int(bool(out_fp32)), int(cin_total), int(cin_offset))
+    stage = _STAGE.get(conv_path(x, g, 0), "styleunet_conv_direct")
+    stats.add_work(stage, _flops(g))
+    with torch.cuda.device(x.device), stats.stage(stage, launches=1):
+        _check(lib.agr_conv2d_forward(_code(x), C.byref(g), _ptr(x), _ptr(w), _ptr(y), C.byref(ep), _stream(x)), "agr_conv2d_forward")
     return y
 
 
-class _ConvAct(torch.autograd.Function):
-    """y = act(conv_same(x, w) + noise_w * noise + bias): forward and data gradient on the tcgen05 implicit-GEMM
-    kernel (epilogue fused), weight gradient still through cuDNN."""
+def weight_transpose(w):
+    """KRSC (Cout,Cin,k,k) channels_last -> (Cin,Cout,k,k) channels_last: the operand of the data-gradient calls."""
+    lib = _lib.load()
+    Cout, Cin, k = w.shape[0], w.shape[1], w.shape[-1]
+    wt = torch.empty((Cin, Cout, k, k), dtype=w.dtype, device=w.device, memory_format=_CL)
+    with torch.cuda.device(w.device), stats.stage("styleunet_weight", launches=1):
+        _check(lib.agr_weight_transpose(_code(w), _ptr(w), _ptr(wt), Cout, Cin, k, _stream(w)), "agr_weight_transpose")
+    return wt
+
+
+def conv_dgrad(dy, wt, g):
+    """dx (N,Cin,H,W) of the layer `g` from dy (N,Cout,OH,OW) and wt = weight_transpose(w)."""
+    lib = _lib.load()
+    dx = torch.empty((g.N, g.Cin, g.H, g.W), dtype=dy.dtype, device=dy.device, memory_format=_CL)
+    stage = _STAGE.get(conv_path(dy, g, 1), "styleunet_conv_direct")
+    stats.add_work(stage, _flops(g))
+    with torch.cuda.device(dy.device), stats.stage(stage, launches=1):
+        _check(lib.agr_conv2d_dgrad(_code(dy), C.byref(g), _ptr(dy), _ptr(wt), _ptr(dx), _stream(dy)), "agr_conv2d_dgrad")
+    return dx
+
+
+def conv_wgrad(x, dy, g, dw=None, ci_total=0, ci_offset=0):
+    """fp32 weight gradient as a (Cout, k, k, ci_total or Cin) buffer (= KRSC memory).  `dw` given: accumulate into it."""
+    lib = _lib.load()
+    ct = int(ci_total) if ci_total else g.Cin
+    zero = dw is None
+    if dw is None:
+        dw = torch.empty((g.Cout, g.ksize, g.ksize, ct), dtype=torch.float32, device=x.device)
+    stage = _STAGE.get(conv_path(x, g, 2), "styleunet_conv_direct")
+    stats.add_work(stage, _flops(g))
+    with torch.cuda.device(x.device), stats.stage(stage, launches=1 + int(zero)):
+        _check(lib.agr_conv2d_wgrad(_code(x), C.byref(g), _ptr(x), _ptr(dy), _ptr(dw), ct, int(ci_offset), int(zero), _stream(x)),
+               "agr_conv2d_wgrad")
+    return dw
+
+
+def _as_kcrs(dw):
+    """(Cout,k,k,Cin) buffer -> logical (Cout,Cin,k,k) tensor in channels_last memory (no copy)."""
+    return dw.permute(0, 3, 1, 2)
+
+
+def _act_backward(g, y, nz, activate, has_b, has_n, Cout):
+    """Gradient through act(z + noise_w*noise + bias): dz, d_bias, d_noise_w (one pass; reductions by atomics)."""
+    lib = _lib.load()
+    if not (activate or has_b or has_n):
+        return g, None, None
+    pixels = g.numel() // Cout
+    dz = torch.empty_like(g)
+    db = _zeros(Cout, g.device) if has_b else None
+    dn = _zeros(1, g.device) if has_n else None
+    with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
+        _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dz), pixels, Cout, _ptr(nz) if has_n else None,
+                                         nz.numel() if has_n else 1, _ptr(db), _ptr(dn), int(activate), _stream(g)),
+               "agr_bias_act_backward")
+    return dz, db, dn
+
+
+class _Conv(torch.autograd.Function):
+    """y = act(conv(x, w) + noise_w * noise + bias) for every layer geometry of the path (include/agr_conv.h): forward,
+    data gradient and weight gradient on the tcgen05 kernels (bf16, channel counts that are multiples of 64) or the
+    CUDA-core kernels (fp32 parity mode, narrow layers).  `w` is the conv-ready KRSC operand; its gradient is produced
+    in fp32 and handed to `handle` when the operand comes from a weight plan (see _ModWeightGroup), to `w` otherwise."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, noise, noise_weight, activate):
+    def forward(ctx, x, w, handle, bias, noise, noise_weight, activate, k, stride, pad, transposed):
         x = _nhwc(x)
         w = w.contiguous(memory_format=_CL)
-        Cout, k = w.shape[0], w.shape[-1]
+        if w.dtype != x.dtype:
+            raise RuntimeError("conv: weight operand %s does not match the activation dtype %s" % (w.dtype, x.dtype))
+        g = conv_geom(x.shape, w.shape[0], k, stride, pad, transposed)
         b = bias.detach().float().contiguous() if bias is not None else None
         nz = noise.detach().float().contiguous() if noise is not None else None
         nw = noise_weight.detach().float().contiguous() if noise_weight is not None else None
-        y = _tc_conv(x, w, Cout, k, b, nz, nw if nz is not None else None, activate)
+        y = conv_forward(x, w, g, b, nz, nw, activate)
         ctx.save_for_backward(x, w, y if activate else None, nz)
-        ctx.meta = (activate, k, bias is not None, noise is not None and noise_weight is not None,
-                    None if bias is None else bias.shape, None if noise_weight is None else noise_weight.shape)
+        ctx.g = g
+        ctx.meta = (int(activate), bias is not None, noise is not None and noise_weight is not None,
+                    None if bias is None else bias.shape, None if noise_weight is None else noise_weight.shape, handle is not None)
         return y
 
     @staticmethod
-    def backward(ctx, g):
-        lib = _lib.load()
+    def backward(ctx, gy):
         x, w, y, nz = ctx.saved_tensors
-        activate, k, has_b, has_n, bshape, nshape = ctx.meta
-        Cout, Cin = w.shape[0], w.shape[1]
-        g = _nhwc(g)
-        pixels = g.shape[0] * g.shape[2] * g.shape[3]
-        if activate or has_b or has_n:
-            dz = torch.empty_like(g)
-            db = _zeros(Cout, g.device) if has_b else None
-            dn = _zeros(1, g.device) if has_n else None
-            with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
-                _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dz), pixels, Cout, _ptr(nz) if has_n else None,
-                                                 nz.numel() if has_n else 1, _ptr(db), _ptr(dn), int(activate), _stream(g)),
-                       "agr_bias_act_backward")
-        else:
-            dz, db, dn = g, None, None
+        activate, has_b, has_n, bshape, nshape, has_handle = ctx.meta
+        g = ctx.g
+        gy = _nhwc(gy)
+        dz, db, dn = _act_backward(gy, y, nz, activate, has_b, has_n, g.Cout)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            if lib.agr_conv2d_tc_supported(g.shape[2], g.shape[3], Cout, Cin, k):
-                wt = torch.empty((Cin, Cout, k, k), dtype=w.dtype, device=w.device, memory_format=_CL)
-                with torch.cuda.device(g.device), stats.stage("styleunet_weight", launches=1):
-                    _check(lib.agr_weight_flip_transpose(_ptr(w), _ptr(wt), Cout, Cin, k, _stream(g)), "agr_weight_flip_transpose")
-                dx = _tc_conv(dz, wt, Cin, k, None, None, None, False)
-            else:
-                dx = torch.ops.aten.convolution_backward(dz, x, w, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
-                                                         [True, False, False])[0]
-        if ctx.needs_input_grad[1]:
-            dw = torch.ops.aten.convolution_backward(dz, x, w, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
-                                                     [False, True, False])[1]
-        return dx, dw, (db.view(bshape) if has_b else None), None, (dn.view(nshape) if has_n else None), None
+            dx = conv_dgrad(dz, weight_transpose(w), g)
+        if ctx.needs_input_grad[2 if has_handle else 1]:
+            dw = _as_kcrs(conv_wgrad(x, dz, g))
+        return (dx, None if has_handle else dw, dw if has_handle else None, (db.view(bshape) if has_b else None), None,
+                (dn.view(nshape) if has_n else None), None, None, None, None, None)
 
 
-def _tc_conv_split(x, w, Cout, k, cin_total, cin_offset, residual, bias, activate, out_fp32=False):
-    lib = _lib.load()
-    y = torch.empty((x.shape[0], Cout, x.shape[2], x.shape[3]), dtype=torch.float32 if out_fp32 else x.dtype, device=x.device,
-                    memory_format=_CL)
-    stats.add_work("styleunet_conv_tc", 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * x.shape[1] * Cout * k * k)
-    with torch.cuda.device(x.device), stats.stage("styleunet_conv_tc", launches=1):
-        _check(lib.agr_conv2d_tc_forward_split(_ptr(x), _ptr(w), _ptr(y), int(out_fp32), x.shape[0], x.shape[2], x.shape[3], x.shape[1], Cout, k,
-                                               cin_total, cin_offset, _ptr(residual), _ptr(bias), int(activate), _stream(x)),
-               "agr_conv2d_tc_forward_split")
-    return y
+def conv2d(x, w, handle=None, bias=None, noise=None, noise_weight=None, activate=0, k=None, stride=1, pad=None, transposed=False):
+    k = int(w.shape[-1]) if k is None else k
+    pad = k // 2 if pad is None else pad
+    return _Conv.apply(x, w, handle, bias, noise, noise_weight, int(activate), k, int(stride), int(pad), bool(transposed))
 
 
 class _SplitConvAct(torch.autograd.Function):
@@ -850,88 +924,87 @@ class _SplitConvAct(torch.autograd.Function):
     half conv(b, w[:, Ca:]) runs once and enters the per-view half as a residual in the tcgen05 epilogue."""
 
     @staticmethod
-    def forward(ctx, a, b, w, bias, activate):
+    def forward(ctx, a, b, w, handle, bias, activate):
         a, b = _nhwc(a), _nhwc(b)
         w = w.contiguous(memory_format=_CL)
         Cout, k, Ca, Cb = w.shape[0], w.shape[-1], a.shape[1], b.shape[1]
         bb = bias.detach().float().contiguous() if bias is not None else None
-        zb = _tc_conv_split(b, w, Cout, k, Ca + Cb, Ca, None, None, False, out_fp32=True)   # fp32 partial sum
-        y = _tc_conv_split(a, w, Cout, k, Ca + Cb, 0, zb, bb, activate)
+        ga, gb = conv_geom(a.shape, Cout, k), conv_geom(b.shape, Cout, k)
+        zb = conv_forward(b, w, gb, out_fp32=True, cin_total=Ca + Cb, cin_offset=Ca)   # fp32 partial sum
+        y = conv_forward(a, w, ga, bb, None, None, activate, residual=zb, cin_total=Ca + Cb, cin_offset=0)
         ctx.save_for_backward(a, b, w, y if activate else None)
-        ctx.meta = (activate, k, bias is not None, None if bias is None else bias.shape)
+        ctx.geoms = (ga, gb)
+        ctx.meta = (int(activate), k, bias is not None, None if bias is None else bias.shape, handle is not None)
         return y
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
         a, b, w, y = ctx.saved_tensors
-        activate, k, has_b, bshape = ctx.meta
+        activate, k, has_b, bshape, has_handle = ctx.meta
+        ga, gb = ctx.geoms
         Cout, Ca, Cb, V = w.shape[0], a.shape[1], b.shape[1], a.shape[0]
         g = _nhwc(g)
-        pixels = g.shape[0] * g.shape[2] * g.shape[3]
-        dz = torch.empty_like(g)
-        db = _zeros(Cout, g.device) if has_b else None
-        with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
-            _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dz), pixels, Cout, None, 1, _ptr(db), None,
-                                             int(activate), _stream(g)), "agr_bias_act_backward")
+        dz, db, _ = _act_backward(g, y, None, activate, has_b, False, Cout)
         dzs = _new_like(dz[:1], Cout, dz.shape[2], dz.shape[3])
         with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
             _check(lib.agr_sum_batch(_code(dz), _ptr(dz), _ptr(dzs), V, dzs.numel(), _stream(g)), "agr_sum_batch")
-        wt = torch.empty((Ca + Cb, Cout, k, k), dtype=w.dtype, device=w.device, memory_format=_CL)
-        with torch.cuda.device(g.device), stats.stage("styleunet_weight", launches=1):
-            _check(lib.agr_weight_flip_transpose(_ptr(w), _ptr(wt), Cout, Ca + Cb, k, _stream(g)), "agr_weight_flip_transpose")
-        da = _tc_conv(dz, wt[:Ca], Ca, k, None, None, None, False) if ctx.needs_input_grad[0] else None
-        dbb = _tc_conv(dzs, wt[Ca:], Cb, k, None, None, None, False) if ctx.needs_input_grad[1] else None
+        wt = weight_transpose(w)                       # (Ca+Cb, Cout, k, k): rows = input channels
+        da = conv_dgrad(dz, wt[:Ca], ga) if ctx.needs_input_grad[0] else None
+        dbb = conv_dgrad(dzs, wt[Ca:], gb) if ctx.needs_input_grad[1] else None
         dw = None
-        if ctx.needs_input_grad[2]:
-            pad = [k // 2, k // 2]
-            dwa = torch.ops.aten.convolution_backward(dz, a, w[:, :Ca], None, [1, 1], pad, [1, 1], False, [0, 0], 1, [False, True, False])[1]
-            dwb = torch.ops.aten.convolution_backward(dzs, b, w[:, Ca:], None, [1, 1], pad, [1, 1], False, [0, 0], 1, [False, True, False])[1]
-            dw = torch.cat([dwa, dwb], 1).contiguous(memory_format=_CL)
-        return da, dbb, dw, (db.view(bshape) if has_b else None), None
+        if ctx.needs_input_grad[3 if has_handle else 2]:
+            dwf = conv_wgrad(a, dz, ga, ci_total=Ca + Cb, ci_offset=0)
+            conv_wgrad(b, dzs, gb, dw=dwf, ci_total=Ca + Cb, ci_offset=Ca)
+            dw = _as_kcrs(dwf)
+        return da, dbb, None if has_handle else dw, dw if has_handle else None, (db.view(bshape) if has_b else None), None
+
+
+def _operand(weight, s, scale, demodulate, dtype):
+    """-> (conv-ready KRSC operand, gradient handle or None)."""
+    hit = planned_weight(weight, dtype)
+    if hit is not None:
+        return hit
+    return mod_weight(weight, s, scale, demodulate, dtype)
 
 
 def equal_conv2d_split(a, b, weight, scale, act_bias=None, activate=True):
     """ConvLayer on cat([a, b], 1) where b (batch 1) is shared by the batch of a; falls back to the plain path when the
-    shapes are outside the tensor-core kernel's coverage."""
+    shapes are outside the tensor-core kernel's coverage (the split needs its fp32 residual epilogue)."""
     Ca, Cb = a.shape[1], b.shape[1]
     k = weight.shape[-1]
-    ok = (a.dtype == torch.bfloat16 and b.shape[0] == 1 and Ca % 64 == 0 and Cb % 64 == 0 and
-          _lib.load().agr_conv2d_tc_supported(a.shape[2], a.shape[3], Ca, weight.shape[0], k) and
-          _lib.load().agr_conv2d_tc_supported(a.shape[2], a.shape[3], Cb, weight.shape[0], k))
+    ok = (b.shape[0] == 1 and Ca % 64 == 0 and Cb % 64 == 0 and a.dtype == torch.bfloat16 and
+          conv_path(a, conv_geom(a.shape, weight.shape[0], k), 0) == 1 and conv_path(b, conv_geom(b.shape, weight.shape[0], k), 0) == 1)
     if not ok:
         return equal_conv2d(torch.cat([a, expand_batch(b, a.shape[0])], 1), weight, scale, 1, k // 2, act_bias, activate)
-    w = _prepared(weight, None, scale, False, False, a.dtype)
-    return _SplitConvAct.apply(a, b, w, act_bias, activate)
+    w, handle = _operand(weight, None, scale, False, a.dtype)
+    return _SplitConvAct.apply(a, b, w, handle, act_bias, int(bool(activate)))
 
 
 def equal_conv2d(x, weight, scale, stride, padding, act_bias=None, activate=True):
-    w = _prepared(weight, None, scale, False, False, x.dtype)
-    if _tc_ok(x, w.shape[0], w.shape[-1], stride) and padding == w.shape[-1] // 2:
-        return _ConvAct.apply(x, w, act_bias, None, None, activate)
-    out = F.conv2d(x, w, None, stride=stride, padding=padding)
-    if act_bias is None and not activate:
-        return out
-    return bias_act(out, act_bias, activate=activate)
+    """EqualConv2d [+ FusedLeakyReLU] (dual_styleunet.py:93-122, 329-371) as one fused op."""
+    w, handle = _operand(weight, None, scale, False, x.dtype)
+    return conv2d(x, w, handle, bias=act_bias, activate=int(bool(activate)), stride=stride, pad=padding)
 
 
 def modulated_conv2d(x, weight, s, scale, demodulate=True, upsample=False, downsample=False, blur=None, padding=1,
                      noise=None, noise_weight=None, act_bias=None, activate=True):
-    """`s` may be a callable returning the (1, Cin) style modulation: it is only evaluated when no weight plan holds
-    this layer's operand."""
-    w = planned_weight(weight, x.dtype)
-    if w is None:
+    """ModulatedConv2d's fused branch (dual_styleunet.py:256-300) + NoiseInjection + FusedLeakyReLU.  `s` may be a
+    callable returning the (1, Cin) style modulation: it is only evaluated when no weight plan holds this layer's operand."""
+    hit = planned_weight(weight, x.dtype)
+    if hit is None:
         if callable(s):
             s = s()
         if s.shape[0] != 1:
             raise RuntimeError("one style per call: the batch (views of one pose) shares the modulated weight")
-        w = _ModWeight.apply(weight, s, scale, demodulate, upsample, x.dtype)
-    if upsample:
-        out = blur(F.conv_transpose2d(x, w, padding=0, stride=2))
-    elif downsample:
-        out = F.conv2d(blur(x), w, padding=0, stride=2)
+        hit = mod_weight(weight, s, scale, demodulate, x.dtype)
+    w, handle = hit
+    if upsample:      # conv_transpose2d(stride 2) -> Blur -> noise, bias, activation   (dual_styleunet.py:266-282)
+        out = blur(conv2d(x, w, handle, stride=2, pad=0, transposed=True))
+        return bias_act(out, act_bias, noise=noise, noise_weight=noise_weight, activate=activate)
+    if downsample:    # Blur -> conv2d(stride 2)                                          (dual_styleunet.py:283-290)
+        x, stride, padding = blur(x), 2, 0
     else:
-        if _tc_ok(x, w.shape[0], w.shape[-1], 1) and padding == w.shape[-1] // 2:
-            return _ConvAct.apply(x, w, act_bias, noise, noise_weight, activate)
-        out = F.conv2d(x, w, padding=padding)
-    return bias_act(out, act_bias, noise=noise, noise_weight=noise_weight, activate=activate)
+        stride = 1
+    return conv2d(x, w, handle, bias=act_bias, noise=noise, noise_weight=noise_weight, activate=int(bool(activate)),
+                  stride=stride, pad=padding)

@@ -8,8 +8,7 @@
  *                        (network/styleunet/upfirdn2d.cpp:17-30, upfirdn2d_kernel.cu:49-369)
  *   ModulatedConv2d weight preparation (dual_styleunet.py:256-265), NoiseInjection (:303-313),
  *   HaarTransform / InverseHaarTransform (:387-425).
- * and holds the dense 3x3 / 1x1 contraction (implicit GEMM on tcgen05) that replaces the cuDNN calls
- * (conv2d_gradfix.py:34,66).
+ * The dense contractions that replace the cuDNN calls (conv2d_gradfix.py:34,66) live in agr_conv.h.
  *
  * dtype: AGR_F32 = 0, AGR_BF16 = 1 (activations; reductions / parameters stay fp32).
  * Layout: activations are NHWC (torch channels_last), i.e. x[n][h][w][c] contiguous in c.
@@ -39,13 +38,13 @@ int agr_upfirdn2d(int32_t dtype, const void* x, void* y, int32_t N, int32_t H, i
 int agr_haar(int32_t dtype, int32_t mode, const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
              void* cuda_stream);
 
-/* y = act(x + noise_w[0] * noise[n? no: h][w] + bias[c]),  act = lrelu(.,0.2)*sqrt(2) if activate else identity.
+/* y = act(x + noise_w[0] * noise[h][w] + bias[c]),  act = identity (activate 0) | lrelu(.,0.2)*sqrt(2) (1) | lrelu(.,0.2) (2).
  * noise: (H,W) fp32 or NULL, indexed with pixel % noise_period (= H*W: one noise image shared by the batch);
  * noise_w: 1 fp32 on device or NULL; bias: (C) fp32 or NULL. */
 int agr_bias_act_forward(int32_t dtype, const void* x, void* y, int64_t pixels, int32_t C, const float* bias,
                          const float* noise, const float* noise_w, int64_t noise_period, int32_t activate,
                          void* cuda_stream);
-/* dx = dy * (activate ? (y > 0 ? sqrt2 : 0.2*sqrt2) : 1); d_bias[c] += sum dx; d_noise_w[0] += sum dx*noise.
+/* dx = dy * (activate ? (y > 0 ? gain : 0.2*gain) : 1), gain = sqrt2 (activate 1) or 1 (activate 2); d_bias[c] += sum dx; d_noise_w[0] += sum dx*noise.
  * d_bias / d_noise_w (fp32) are ACCUMULATED into (caller zeroes); either may be NULL. y is the forward OUTPUT. */
 int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx, int64_t pixels, int32_t C,
                           const float* noise, int64_t noise_period, float* d_bias, float* d_noise_w, int32_t activate,
@@ -82,36 +81,8 @@ typedef struct AgrModWeightItem {
 int agr_modweight_group_forward(int32_t dtype, const AgrModWeightItem* items, int32_t count, void* cuda_stream);
 int agr_modweight_group_backward(int32_t dtype, const AgrModWeightItem* items, int32_t count, void* cuda_stream);
 
-/* ---- dense contraction on the tensor cores (tcgen05.mma + TMA, bf16 in / fp32 accumulate / bf16 out) ----
- * Stride-1 "same" convolution, NHWC, N images sharing one weight (the view batch of the colour-net tail):
- *   y = act(conv(x, w) + noise_w*noise + bias).
- *   x (N,H,W,Cin) bf16, w_krsc (Cout, k, k, Cin) bf16 (what agr_modweight_forward writes), y (N,H,W,Cout) bf16,
- *   bias (Cout) fp32 / noise (H,W) fp32 (shared by the N images) / noise_w (1) fp32 may be NULL; activate: lrelu(0.2)*sqrt(2).
- * Shapes must satisfy agr_conv2d_tc_supported (H % 8 == 0, W % 16 == 0, Cin % 64 == 0, Cout % 64 == 0, k in {1,3}).
- * The data gradient of the same convolution is this call on dy with agr_weight_flip_transpose(w). */
-int agr_conv2d_tc_supported(int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);
-int agr_conv2d_tc_forward(const void* x, const void* w_krsc, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin,
-                          int32_t Cout, int32_t ksize, const float* bias, const float* noise, const float* noise_w,
-                          int32_t activate, void* cuda_stream);
-/* Split-K form for the coarse decoder levels (16x16 ... 64x64 maps with 512 channels: 2-128 output tiles, one CTA each
- * walking up to 72 (tap, channel-block) steps -- latency-bound at ~33 us on 2-128 of the 148 SMs).  `splits` CTAs share an
- * output tile, each contracting a contiguous slice of the (tap, channel-block) loop and adding its fp32 partial tile
- * into `workspace` (N*H*W*Cout floats, zeroed here); a second small kernel applies noise / bias / activation and
- * writes bf16 y.  agr_conv2d_tc_splits returns the split count this library would choose (1 = use the plain call). */
-int agr_conv2d_tc_splits(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);
-int agr_conv2d_tc_forward_splitk(const void* x, const void* w_krsc, void* y, float* workspace, int32_t splits, int32_t N,
-                                 int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, const float* bias,
-                                 const float* noise, const float* noise_w, int32_t activate, void* cuda_stream);
-/* Same kernel contracting x (N,H,W,Cin) with the input-channel SLICE [w_cin_offset, w_cin_offset+Cin) of a wider weight
- * (Cout,k,k,w_cin_total) and adding `residual` (H,W,Cout) fp32 (shared by the N images) before bias / activation;
- * out_fp32 != 0 stores the raw fp32 accumulator in y (N,H,W,Cout fp32) — the partial sum the second half consumes:
- *   conv(cat([a_v, b]), w) = conv(a_v, w[.., :Ca]) + conv(b, w[.., Ca:])
- * so the skip concatenation of the colour-net tail (dual_styleunet.py:875-876) never materialises and the
- * view-independent half is computed once for all V views. */
-int agr_conv2d_tc_forward_split(const void* x, const void* w_krsc, void* y, int32_t out_fp32, int32_t N, int32_t H,
-                                int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t w_cin_total,
-                                int32_t w_cin_offset, const float* residual, const float* bias, int32_t activate,
-                                void* cuda_stream);
+/* The dense contractions (every convolution of the path, forward / data gradient / weight gradient) are declared in
+ * agr_conv.h. */
 
 /* View-feature injection of the colour net (dual_styleunet.py:881-883,900-902):
  *   y[v] = base[v or 0] + bilinear_2x(vf[v])      F.interpolate(mode='bilinear', align_corners=False), exact 2x
@@ -168,9 +139,6 @@ typedef struct AgrEqualLinearItem {
 } AgrEqualLinearItem;
 int agr_equal_linear_group_forward(const AgrEqualLinearItem* items, int32_t count, void* cuda_stream);
 int agr_equal_linear_group_backward(const AgrEqualLinearItem* items, int32_t count, void* cuda_stream);
-
-/* w_out[ci][k*k-1-t][co] = w_krsc[co][t][ci]  (bf16) */
-int agr_weight_flip_transpose(const void* w_krsc, void* w_out, int32_t Cout, int32_t Cin, int32_t ksize, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,7 @@ def test_ctypes_structs_match_the_c_headers(tmp_path):
     import subprocess
     from animatablegaussians_b200 import _lib, styleunet_ops as ops
     structs = {"AgrModWeightItem": (ops.AgrModWeightItem, "agr_styleunet.h"), "AgrEqualLinearItem": (ops.AgrEqualLinearItem, "agr_styleunet.h"),
+               "AgrConvGeom": (ops.AgrConvGeom, "agr_conv.h"), "AgrConvEpilogue": (ops.AgrConvEpilogue, "agr_conv.h"),
                "AgrRasterWorkspace": (_lib.AgrRasterWorkspace, "agr_rasterizer.h"), "AgrRasterForwardArgs": (_lib.AgrRasterForwardArgs, "agr_rasterizer.h"),
                "AgrRasterBackwardArgs": (_lib.AgrRasterBackwardArgs, "agr_rasterizer.h")}
     src = ['#include <stdio.h>', '#include <stddef.h>'] + sorted({'#include "%s"' % h for _, h in structs.values()}) + ["int main(void) {"]
