@@ -20,7 +20,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import contextlib
 import ctypes as C
+import os
 
 from . import _lib, camera, lbs, stats
 from . import styleunet_ops as ops
@@ -149,6 +151,7 @@ class AvatarNet(nn.Module):
         self.opt = opt
         self.random_style = opt.get('random_style', False)
         self.with_viewdirs = opt.get('with_viewdirs', True)
+        self.concurrent_nets = os.environ.get('AGR_SERIAL_NETS', '0') != '1'   # render_views: nets on parallel streams
         if device is None:
             try:
                 import config  # the reference's global config module, when running under main_avatar.py
@@ -348,6 +351,11 @@ class AvatarNet(nn.Module):
         return ret
 
     # ------------------------------------------------------------------ view batch (one pose, V cameras)
+    def _side_streams(self):
+        if getattr(self, "_streams", None) is None:
+            self._streams = (torch.cuda.Stream(self.device_), torch.cuda.Stream(self.device_))
+        return self._streams
+
     def prepare_views(self, extrs, intrs, img_w, img_h, bg_color=(0., 0., 0.), capacity=None):
         """Host-side camera setup for a view batch (everything render3 derives from extr/intr,
         gaussian_renderer.py:44-52, plus the camera centres of get_viewdir_feat, avatar.py:131), uploaded with one
@@ -369,12 +377,21 @@ class AvatarNet(nn.Module):
             views = self.prepare_views(extrs, intrs, img_w, img_h, bg_color)
         V = views["V"]
         pose_map = items['smpl_pos_map'][:3]
-        pf, pb = self.position_net.forward_maps([self.position_style], pose_map[None])
-        cano_pts = 0.05 * self._gather_pair(pf, pb) + self.cano_gaussian_model.get_xyz
+        # The three U-Nets are independent until the rasterizer.  Position and "other" nets (batch 1: 2 - 128 CTAs per
+        # convolution, less than the 148 SMs) run on two side streams next to the colour net, forward AND backward
+        # (autograd replays each node on its forward stream); inside a captured step they become parallel graph branches.
+        main = torch.cuda.current_stream()
+        side = self._side_streams() if (self.concurrent_nets and pose_map.is_cuda) else None
+        if side is not None:
+            for st in side:
+                st.wait_stream(main)
+        with torch.cuda.stream(side[0]) if side is not None else contextlib.nullcontext():
+            pf, pb = self.position_net.forward_maps([self.position_style], pose_map[None])
+            pgather = self._gather_pair(pf, pb)
+        with torch.cuda.stream(side[1]) if side is not None else contextlib.nullcontext():
+            of, ob = self.other_net.forward_maps([self.other_style], pose_map[None])
+            ogather = self._gather_pair(of, ob)
         pos_map = None   # (the (S,2S,3) map view is only produced by render(); the trainer reads it for visualisation)
-        of, ob = self.other_net.forward_maps([self.other_style], pose_map[None])
-        opacity, scales, rotations = self._activate_others(self._gather_pair(of, ob))
-        nonrigid_offset = cano_pts - self.init_points
         if self.with_viewdirs:
             with torch.no_grad():
                 live = lbs.skin_points(self.lbs, items['cano2live_jnt_mats'], self.init_points, self.cano_nmls)
@@ -387,6 +404,13 @@ class AvatarNet(nn.Module):
         else:
             cf, cb = self.color_net.forward_maps([self._color_style()], pose_map[None])
             colors = self._gather_pair(cf, cb)
+        if side is not None:
+            for st, t in zip(side, (pgather, ogather)):
+                main.wait_stream(st)
+                t.record_stream(main)
+        cano_pts = 0.05 * pgather + self.cano_gaussian_model.get_xyz
+        opacity, scales, rotations = self._activate_others(ogather)
+        nonrigid_offset = cano_pts - self.init_points
         pos, rot = lbs.transform_cano2live(self.lbs, items['cano2live_jnt_mats'], cano_pts, rotations)
         color, radii, depth, alpha = rasterize_gaussians_batched(pos, None, None, colors, opacity, scales, rot, None,
                                                                  views["settings"])

@@ -391,8 +391,10 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const T* __restrict__
                 psum += g[i];
             }
             if (noise) nsum += psum * noise[p % nper];
-            if (VECTOR) { typename VecOf<T>::V v; pack(g, v); *reinterpret_cast<typename VecOf<T>::V*>(dx + p * C + my_c) = v; }
-            else dx[p * C + my_c] = from_f<T>(g[0]);
+            if (dx) {   // dx == NULL: identity activation, the caller keeps using dy (only the reductions are wanted)
+                if (VECTOR) { typename VecOf<T>::V v; pack(g, v); *reinterpret_cast<typename VecOf<T>::V*>(dx + p * C + my_c) = v; }
+                else dx[p * C + my_c] = from_f<T>(g[0]);
+            }
         }
         if (d_bias) {
 #pragma unroll
@@ -845,7 +847,7 @@ int agr_bias_act_forward(int32_t dtype, const void* x, void* y, int64_t pixels, 
 
 int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx, int64_t pixels, int32_t C, const float* noise,
                           int64_t noise_period, float* d_bias, float* d_noise_w, int32_t activate, void* cuda_stream) {
-    if (!dy || !dx || (activate && !y) || pixels < 0 || C < 1 || (noise && noise_period < 1)) return AGR_ERR_INVALID_ARGUMENT;
+    if (!dy || (!dx && activate) || (activate && !y) || pixels < 0 || C < 1 || (noise && noise_period < 1)) return AGR_ERR_INVALID_ARGUMENT;
     if (!noise) noise_period = 1;
     if (pixels == 0) return AGR_OK;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);

@@ -36,9 +36,10 @@ def count(n):
 
 
 @contextlib.contextmanager
-def stage(name, launches=0):
+def stage(name, launches=0, label=None):
     """Times the enclosed C-ABI call(s) with CUDA events on the current stream; `launches` = number of OUR
-    kernels the call launches (library kernels such as CUB / cuDNN are not counted)."""
+    kernels the call launches (library kernels such as CUB are not counted).  `label`: optional finer key (a layer
+    geometry) reported under snapshot()["detail"]."""
     if not ENABLED:
         yield
         return
@@ -46,15 +47,21 @@ def stage(name, launches=0):
     e0.record()
     yield
     e1.record()
-    _events.setdefault(name, []).append((e0, e1))
+    _events.setdefault(name, []).append((e0, e1, label))
     count(launches)
 
 
 def snapshot():
     global ENABLED
     torch.cuda.synchronize()
-    out = {"launches": _launches, "stages": {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in _events.items()},
-           "work": dict(_work)}
+    detail = {}
+    for k, v in _events.items():
+        for a, b, lab in v:
+            if lab is not None:
+                ms, n = detail.get(lab, (0.0, 0))
+                detail[lab] = (ms + a.elapsed_time(b), n + 1)
+    out = {"launches": _launches, "stages": {k: (sum(a.elapsed_time(b) for a, b, _ in v), len(v)) for k, v in _events.items()},
+           "work": dict(_work), "detail": detail}
     ENABLED = False
     return out
 
@@ -72,7 +79,7 @@ def roofline_tensor(st, steps, peaks):
     ms, n = st["stages"].get("styleunet_conv_tc", (0.0, 0))
     fl = st.get("work", {}).get("styleunet_conv_tc", 0.0)
     ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-    return {"bound": "tensor", "kernel": "conv_tc_kernel<BN,STAGES> (tcgen05.mma implicit-GEMM 3x3/1x1 conv, fwd + dgrad launches)",
+    return {"bound": "tensor", "kernel": "conv_tc_kernel<BN,STAGES> + conv_wgrad_tc_kernel<MT,NT> (tcgen05.mma implicit-GEMM convolutions: forward, data gradient and weight gradient launches of every layer with Cin, Cout multiples of 64)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": which,
             "launches_per_step": n / max(steps, 1), "algorithmic_flop_per_step": fl / max(steps, 1), "seconds_per_step": ms * 1e-3 / max(steps, 1)}
 

@@ -134,7 +134,7 @@ _arena = None
 def step_arena(chunk_floats=1 << 18):
     """Wrap ONE forward+backward (eager, or the body of a CUDA-graph capture)."""
     global _arena
-    prev, _arena = _arena, {"buf": None, "off": 0, "chunk": int(chunk_floats)}
+    prev, _arena = _arena, {"bufs": {}, "chunk": int(chunk_floats)}
     try:
         yield
     finally:
@@ -142,13 +142,18 @@ def step_arena(chunk_floats=1 << 18):
 
 
 def _zeros(n, dev):
+    """Chunks are per (device, stream): a chunk is zero-filled on the stream that asked for it and only handed to work
+    queued on that same stream (the nets of a step run on parallel streams, forward and backward)."""
     a = _arena
     if a is None or n > a["chunk"]:
         return torch.zeros(n, dtype=torch.float32, device=dev)
-    if a["buf"] is None or a["buf"].device != dev or a["off"] + n > a["chunk"]:
-        a["buf"], a["off"] = torch.zeros(a["chunk"], dtype=torch.float32, device=dev), 0
-    out = a["buf"][a["off"]:a["off"] + n]
-    a["off"] += (n + 3) // 4 * 4   # keep every slice 16-byte aligned
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    slot = a["bufs"].get(key)
+    if slot is None or slot[1] + n > a["chunk"]:
+        slot = [torch.zeros(a["chunk"], dtype=torch.float32, device=dev), 0]
+        a["bufs"][key] = slot
+    out = slot[0][slot[1]:slot[1] + n]
+    slot[1] += (n + 3) // 4 * 4   # keep every slice 16-byte aligned
     return out
 
 
@@ -794,6 +799,10 @@ def conv_geom(x_shape, Cout, k, stride=1, pad=None, transposed=False):
     return AgrConvGeom(N, H, W, Cin, OH, OW, int(Cout), int(k), int(stride), pad, int(bool(transposed)))
 
 
+def _label(what, g):
+    return "%s N%d %dx%d %d->%d k%d s%d%s" % (what, g.N, g.H, g.W, g.Cin, g.Cout, g.ksize, g.stride, " T" if g.transposed else "")
+
+
 def _flops(g):
     pix = g.N * (g.H * g.W if g.transposed else g.OH * g.OW)
     return 2.0 * pix * g.Cin * g.Cout * g.ksize * g.ksize
@@ -812,7 +821,7 @@ def conv_forward(x, w, g, bias=None, noise=None, noise_w=None, activate=0, resid
                          int(bool(out_fp32)), int(cin_total), int(cin_offset))
     stage = _STAGE.get(conv_path(x, g, 0), "styleunet_conv_direct")
     stats.add_work(stage, _flops(g))
-    with torch.cuda.device(x.device), stats.stage(stage, launches=1):
+    with torch.cuda.device(x.device), stats.stage(stage, launches=1, label=_label("fwd", g)):
         _check(lib.agr_conv2d_forward(_code(x), C.byref(g), _ptr(x), _ptr(w), _ptr(y), C.byref(ep), _stream(x)), "agr_conv2d_forward")
     return y
 
@@ -833,7 +842,7 @@ def conv_dgrad(dy, wt, g):
     dx = torch.empty((g.N, g.Cin, g.H, g.W), dtype=dy.dtype, device=dy.device, memory_format=_CL)
     stage = _STAGE.get(conv_path(dy, g, 1), "styleunet_conv_direct")
     stats.add_work(stage, _flops(g))
-    with torch.cuda.device(dy.device), stats.stage(stage, launches=1):
+    with torch.cuda.device(dy.device), stats.stage(stage, launches=1, label=_label("dgrad", g)):
         _check(lib.agr_conv2d_dgrad(_code(dy), C.byref(g), _ptr(dy), _ptr(wt), _ptr(dx), _stream(dy)), "agr_conv2d_dgrad")
     return dx
 
@@ -847,7 +856,7 @@ def conv_wgrad(x, dy, g, dw=None, ci_total=0, ci_offset=0):
         dw = torch.empty((g.Cout, g.ksize, g.ksize, ct), dtype=torch.float32, device=x.device)
     stage = _STAGE.get(conv_path(x, g, 2), "styleunet_conv_direct")
     stats.add_work(stage, _flops(g))
-    with torch.cuda.device(x.device), stats.stage(stage, launches=1 + int(zero)):
+    with torch.cuda.device(x.device), stats.stage(stage, launches=1 + int(zero), label=_label("wgrad", g)):
         _check(lib.agr_conv2d_wgrad(_code(x), C.byref(g), _ptr(x), _ptr(dy), _ptr(dw), ct, int(ci_offset), int(zero), _stream(x)),
                "agr_conv2d_wgrad")
     return dw
@@ -864,14 +873,14 @@ def _act_backward(g, y, nz, activate, has_b, has_n, Cout):
     if not (activate or has_b or has_n):
         return g, None, None
     pixels = g.numel() // Cout
-    dz = torch.empty_like(g)
+    dz = torch.empty_like(g) if activate else None     # identity activation: dz is g itself, only the reductions run
     db = _zeros(Cout, g.device) if has_b else None
     dn = _zeros(1, g.device) if has_n else None
     with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
         _check(lib.agr_bias_act_backward(_code(g), _ptr(g), _ptr(y), _ptr(dz), pixels, Cout, _ptr(nz) if has_n else None,
                                          nz.numel() if has_n else 1, _ptr(db), _ptr(dn), int(activate), _stream(g)),
                "agr_bias_act_backward")
-    return dz, db, dn
+    return (dz if activate else g), db, dn
 
 
 class _Conv(torch.autograd.Function):

@@ -275,6 +275,7 @@ def main():
     # per-stage device times + launch count: a separate EAGER pass (event pairs cannot be recorded inside a graph
     # replay and would perturb the timed region anyway)
     graph, wl.graph = wl.graph, None
+    wl.net.concurrent_nets = False   # one stream: the stage event pairs must not overlap each other
     wl.step(False)
     stats.reset()
 
@@ -295,6 +296,9 @@ def main():
     if rank != 0:
         _exit_multi_rank()
 
+    if os.environ.get("AGR_STAGE_DETAIL"):   # per-layer-geometry device times of the staged pass (stderr)
+        for lab, (t, n) in sorted(st["detail"].items(), key=lambda kv: -kv[1][0]):
+            print("%-46s n/step %5.1f  ms/step %8.4f" % (lab, n / args.steps, t / args.steps), file=sys.stderr)
     ms_step = ms / args.steps
     value = N_VIEWS / (ms_step * 1e-3)
     e2e_value = N_VIEWS / (ms_e2e / args.steps * 1e-3)

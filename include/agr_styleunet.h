@@ -45,7 +45,8 @@ int agr_bias_act_forward(int32_t dtype, const void* x, void* y, int64_t pixels, 
                          const float* noise, const float* noise_w, int64_t noise_period, int32_t activate,
                          void* cuda_stream);
 /* dx = dy * (activate ? (y > 0 ? gain : 0.2*gain) : 1), gain = sqrt2 (activate 1) or 1 (activate 2); d_bias[c] += sum dx; d_noise_w[0] += sum dx*noise.
- * d_bias / d_noise_w (fp32) are ACCUMULATED into (caller zeroes); either may be NULL. y is the forward OUTPUT. */
+ * d_bias / d_noise_w (fp32) are ACCUMULATED into (caller zeroes); either may be NULL. y is the forward OUTPUT.
+ * dx may be NULL when activate == 0 (dx == dy: only the reductions are computed). */
 int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx, int64_t pixels, int32_t C,
                           const float* noise, int64_t noise_period, float* d_bias, float* d_noise_w, int32_t activate,
                           void* cuda_stream);

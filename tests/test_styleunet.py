@@ -223,7 +223,7 @@ _CONV_CASES = [  # N, H, W, Cin, Cout, k, stride, pad, transposed, act, noise
     (1, 256, 256, 64, 64, 3, 1, 1, False, 0, True), (2, 128, 256, 128, 128, 3, 1, 1, False, 0, False),   # no lrelu on 4M outputs: kink flips dominate the max-norm
     (16, 512, 512, 64, 64, 3, 1, 1, False, 0, False),                                                     # the benched top level: 64->64 @512^2 x 16 views
     (1, 8, 8, 512, 512, 3, 1, 1, False, 1, False),                                                        # 8x8 level: tile wider than the map
-    (1, 33, 33, 128, 256, 3, 2, 0, False, 1, False), (1, 129, 129, 256, 512, 3, 2, 0, False, 1, False), (1, 17, 17, 512, 512, 3, 2, 0, False, 1, False),   # blur -> stride 2
+    (1, 33, 33, 128, 256, 3, 2, 0, False, 1, False), (1, 129, 129, 256, 512, 3, 2, 0, False, 0, False), (1, 17, 17, 512, 512, 3, 2, 0, False, 1, False),   # blur -> stride 2
     (1, 8, 8, 512, 512, 3, 2, 0, True, 0, False), (2, 32, 32, 128, 64, 3, 2, 0, True, 0, False), (1, 64, 64, 512, 256, 3, 2, 0, True, 0, False),        # transposed stride 2
     (4, 64, 64, 64, 128, 4, 2, 1, False, 0, False), (4, 128, 128, 1, 64, 4, 2, 1, False, 2, False),                                                     # viewdir_net
     (1, 65, 65, 3, 128, 3, 2, 0, False, 1, False), (1, 32, 32, 3, 128, 1, 1, 0, False, 1, False),                                                       # 3-channel inputs
