@@ -79,14 +79,22 @@ def inverse_sigmoid(x):
 
 def knn_mean_dist2(points, K=3, chunk=2048):
     """Mean squared distance to the K nearest neighbours (excluding self) — what the reference gets from
-    pytorch3d.ops.knn_points(K=4)[0][0, :, 1:].mean(-1) (gaussian_model.py:170). Exact, chunked brute force."""
+    pytorch3d.ops.knn_points(K=4)[0][0, :, 1:].mean(-1) (gaussian_model.py:170).  Chunked brute force.  The expansion
+    |a|^2 + |b|^2 - 2ab only RANKS candidates (in float64 about the centroid: for metre-scale coordinates with mm spacing
+    it cancels to a few percent in fp32); the returned distances are exact differences ((p_i - p_j)^2).sum(), as knn_points
+    computes them."""
     N = points.shape[0]
     out = torch.empty(N, dtype=points.dtype, device=points.device)
-    sq = (points * points).sum(-1)
+    pc = (points - points.mean(0, keepdim=True)).double()
+    sq = (pc * pc).sum(-1)
+    kk = min(2 * (K + 1), N)
     for s in range(0, N, chunk):
-        p = points[s:s + chunk]
-        d2 = (sq[s:s + chunk, None] + sq[None, :] - 2.0 * p @ points.T).clamp_min_(0)
-        vals = torch.topk(d2, K + 1, dim=1, largest=False).values
+        p = pc[s:s + chunk]
+        d2 = sq[s:s + chunk, None] + sq[None, :] - 2.0 * (p @ pc.T)
+        idx = torch.topk(d2, kk, dim=1, largest=False).indices                    # candidates (self included)
+        diff = points[s:s + chunk, None, :] - points[idx]                          # exact, in the input dtype
+        exact = (diff * diff).sum(-1)
+        vals = torch.topk(exact, min(K + 1, kk), dim=1, largest=False).values
         out[s:s + chunk] = vals[:, 1:].mean(-1)
     return out
 
@@ -219,6 +227,52 @@ class AvatarNet(nn.Module):
         return torch.cat([front, back], 3)[0].permute(1, 2, 0)
 
     # ------------------------------------------------------------------ reference methods
+    def generate_mean_hands(self, pose_map=None):
+        """network/avatar.py:52-82: Gaussian attributes of ONE reference pose, later blended over the hand regions
+        (test mode, `fix_hand`).  `pose_map`: (>=3, S/2, S/2) posed position map; None reads the map the reference reads,
+        <data_dir>/smpl_pos_map/<fix_hand_id>.exr through the trainer's `config` module (main_avatar.py:583-584)."""
+        lbs_argmax = self.lbs.argmax(1)
+        self.hand_mask = torch.logical_or(torch.logical_or(lbs_argmax == 20, lbs_argmax == 21), lbs_argmax >= 25)
+        if pose_map is None:
+            import glob
+            import cv2 as cv
+            import config
+            paths = sorted(glob.glob(config.opt['train']['data']['data_dir'] + '/smpl_pos_map/%08d.exr' % config.opt['test']['fix_hand_id']))
+            m = cv.imread(paths[0], cv.IMREAD_UNCHANGED)
+            half = m.shape[1] // 2
+            m = np.concatenate([m[:, :half], m[:, half:]], 2).transpose((2, 0, 1))
+            pose_map = torch.from_numpy(m).to(torch.float32).to(self.device_)
+        pose_map = pose_map[:3]
+        self.hand_positions = self.get_positions(pose_map)
+        self.hand_opacity, self.hand_scales, self.hand_rotations = self.get_others(pose_map)
+        self.hand_colors, _ = self.get_colors(pose_map)
+
+    def _fix_hand_active(self):
+        """render()'s `fix_hand` switch: the trainer's config (network/avatar.py:187) or an explicit opt / attribute."""
+        if self.training:
+            return False
+        if self.opt.get('fix_hand', False) or getattr(self, 'fix_hand', False):
+            return True
+        cfg = __import__('sys').modules.get('config')
+        o = getattr(cfg, 'opt', None) if cfg is not None else None
+        return bool(o and o.get('mode') == 'test' and o.get('test', {}).get('fix_hand', False))
+
+    def _blend_hands(self, items, cano_pts, opacity, scales, rotations):
+        """network/avatar.py:187-205 (utils/geo_util.py:104-114 normalize_vert_bbox, per-axis): soft box weights around
+        the canonical MANO vertices, zeroed below the body centre, blending the mean-hand attributes in."""
+        def nbox(verts):
+            lo, hi = verts.min(0, keepdim=True)[0], verts.max(0, keepdim=True)[0]
+            return 2 * (self.init_points - 0.5 * (hi + lo)) / (hi - lo)
+        wl = torch.sigmoid(2.5 * (nbox(items['left_cano_mano_v'])[..., 0:1] + 2.0))
+        wr = torch.sigmoid(-2.5 * (nbox(items['right_cano_mano_v'])[..., 0:1] - 2.0))
+        below = self.init_points[..., 1] < items['cano_smpl_center'][1]
+        wl[below] = 0.
+        wr[below] = 0.
+        s = torch.maximum(wl + wr, torch.ones_like(wl))
+        w = wl / s + wr / s
+        return (w * self.hand_positions + (1.0 - w) * cano_pts, w * self.hand_opacity + (1.0 - w) * opacity,
+                w * self.hand_scales + (1.0 - w) * scales, w * self.hand_rotations + (1.0 - w) * rotations)
+
     def transform_cano2live(self, gaussian_vals, items):
         pos, rot = lbs.transform_cano2live(self.lbs, items['cano2live_jnt_mats'], gaussian_vals['positions'],
                                            gaussian_vals['rotations'])
@@ -339,6 +393,8 @@ class AvatarNet(nn.Module):
         else:
             front_viewdirs, back_viewdirs = None, None
         colors, color_map = self.get_colors(pose_map, front_viewdirs, back_viewdirs)
+        if self._fix_hand_active():
+            cano_pts, opacity, scales, rotations = self._blend_hands(items, cano_pts, opacity, scales, rotations)
         gaussian_vals = {'positions': cano_pts, 'opacity': opacity, 'scales': scales, 'rotations': rotations,
                          'colors': colors, 'max_sh_degree': self.max_sh_degree}
         nonrigid_offset = gaussian_vals['positions'] - self.init_points

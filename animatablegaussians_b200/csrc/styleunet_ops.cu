@@ -407,6 +407,29 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const T* __restrict__
     if (d_noise_w && noise && threadIdx.x == 0) atomicAdd(d_noise_w, s_red[C]);
 }
 
+// ---- the reference's `fused.fused_bias_act` op, element for element (fused_bias_act_kernel.cu:18-65): any contiguous
+// layout, bias indexed (i / step_b) % size_b, act in {1 linear, 3 lrelu}, grad in {0, 1, 2}.  The StyleUNet of this package
+// uses the NHWC kernels above; this entry point exists so that the reference's own fused_act.py runs on this library.
+template <typename T>
+__global__ void __launch_bounds__(256) fused_bias_act_ref_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ b,
+                                                                const T* __restrict__ ref, int act, int grad, float alpha, float scale,
+                                                                int64_t size_x, int64_t step_b, int64_t size_b) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size_x; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = to_f(x[i]);
+        if (b) v += to_f(b[(i / step_b) % size_b]);
+        const float r = ref ? to_f(ref[i]) : 0.f;
+        float y;
+        switch (act * 10 + grad) {
+            default:
+            case 10: case 11: y = v; break;
+            case 12: case 32: y = 0.f; break;
+            case 30: y = v > 0.f ? v : v * alpha; break;
+            case 31: y = r > 0.f ? v : v * alpha; break;
+        }
+        out[i] = from_f<T>(y * scale);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ modweight
 // One block per output channel. w: (Cout, Cin, k, k) fp32.  Row bodies are shared by the per-layer kernels and the
 // grouped kernels (one launch for many layers).
@@ -821,6 +844,21 @@ int agr_wavelet_upsample(int32_t dtype, int32_t adjoint, const void* x, void* y,
         if (adjoint) wavelet_up_bwd_kernel<float><<<g, 256, 0, s>>>((const float*)x, (float*)y, N, h, w, Ci, kp);
         else wavelet_up_fwd_kernel<float><<<g, 256, 0, s>>>((const float*)x, (float*)y, N, h, w, Ci, kp);
     }
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+int agr_fused_bias_act(int32_t dtype, const void* x, const void* bias, const void* refer, void* out, int64_t size_x, int64_t step_b,
+                       int64_t size_b, int32_t act, int32_t grad, float alpha, float scale, void* cuda_stream) {
+    if (!x || !out || size_x < 0 || (bias && (step_b < 1 || size_b < 1)) || (act != 1 && act != 3) || grad < 0 || grad > 2) return AGR_ERR_INVALID_ARGUMENT;
+    if (size_x == 0) return AGR_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    int64_t g = (size_x + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+    if (dtype == AGR_BF16) {
+        using T = __nv_bfloat16;
+        fused_bias_act_ref_kernel<T><<<(unsigned)g, 256, 0, s>>>((T*)out, (const T*)x, (const T*)bias, (const T*)refer, act, grad, alpha, scale, size_x, step_b, size_b);
+    } else if (dtype == AGR_F32) {
+        fused_bias_act_ref_kernel<float><<<(unsigned)g, 256, 0, s>>>((float*)out, (const float*)x, (const float*)bias, (const float*)refer, act, grad, alpha, scale, size_x, step_b, size_b);
+    } else return AGR_ERR_INVALID_ARGUMENT;
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 

@@ -45,6 +45,7 @@ _lib.register_symbols({
     "agr_modweight_group_backward": (C.c_int, [C.c_int32, C.POINTER(AgrModWeightItem), C.c_int32, _p]),
     "agr_upfirdn2d": (C.c_int, [C.c_int32, _p, _p] + [C.c_int32] * 6 + [C.POINTER(C.c_float)] + [C.c_int32] * 6 + [_p]),
     "agr_haar": (C.c_int, [C.c_int32, C.c_int32, _p, _p] + [C.c_int32] * 4 + [_p]),
+    "agr_fused_bias_act": (C.c_int, [C.c_int32, _p, _p, _p, _p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, _p]),
     "agr_bias_act_forward": (C.c_int, [C.c_int32, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, _p]),
     "agr_bias_act_backward": (C.c_int, [C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, _p, C.c_int64, _p, _p, C.c_int32, _p]),
     "agr_modweight_forward": (C.c_int, [C.c_int32, _p, _p, C.c_float] + [C.c_int32] * 5 + [_p, _p, _p]),

@@ -81,7 +81,7 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ product arm
 class ProductWorkload:
-    def __init__(self, rank, world, device):
+    def __init__(self, rank, world, device, lr=1e-7):
         from animatablegaussians_b200 import avatar, optim, synthetic as S, styleunet_ops as ops
         self.rank, self.world, self.dev = rank, world, device
         torch.manual_seed(31359)
@@ -93,7 +93,7 @@ class ProductWorkload:
         # lr: the reference uses 5e-4 (main_avatar.py:45-51).  With the synthetic "sum of outputs" loss that rate walks the
         # random-init nets away from the emulated pre-trained state within a few steps (Gaussians grow until they fill
         # the screen), so the workload would not be stationary.  The Adam arithmetic does not depend on lr.
-        self.opt = optim.FlatAdam(self.net.parameters(), lr=1e-7)
+        self.opt = optim.FlatAdam(self.net.parameters(), lr=lr)
         extrs, Ks = S.ring_cameras(N_VIEWS, img=IMG)
         self.views = list(range(rank, N_VIEWS, world))
         self.extrs, self.Ks = [extrs[v] for v in self.views], [Ks[v] for v in self.views]
@@ -123,8 +123,9 @@ class ProductWorkload:
         items = {"smpl_pos_map": self.d_pose, "cano2live_jnt_mats": self.d_mats}
         out = self.net.render_views(items, return_depth=True, views=self.views_dev)
         # plain sums so that colour, depth AND alpha receive gradients + offset regulariser
+        # (the view-independent regulariser is split over the ranks: the summed gradient is the 1-GPU gradient)
         loss = (out["rgb_maps"].sum() + out["depth_maps"].sum() + out["mask_maps"].sum()) * (1.0 / (IMG * IMG)) \
-            + 0.005 * torch.linalg.norm(out["offset"], dim=-1).mean()
+            + (0.005 / self.world) * torch.linalg.norm(out["offset"], dim=-1).mean()
         loss.backward()
         if self.world > 1:
             self.opt.all_reduce()
@@ -169,6 +170,7 @@ class ProductWorkload:
             st.projmatrix.copy_(self.h_cam[:, 16:32].reshape(V, 4, 4), non_blocking=True)
             st.campos.copy_(self.h_cam[:, 32:35], non_blocking=True)
         if self.graph is not None:
+            self.opt.refresh_hyper()       # lr schedule: the captured step re-reads the pinned {lr, grad_scale} pair
             self.graph.replay()
             loss = self.static_loss
         else:
@@ -224,6 +226,56 @@ def cpu_baseline_sample(n_views=2):
                       "its CUDA ops and its Python cannot travel to the GPU box)" % n_views}
 
 
+def run_check(args, rank, world, device):
+    """--check: ONE eager train step from the seeded initial state (eval mode: no view-direction noise, so every world size
+    sees the same inputs), then the loss, the gradient bucket and the parameter delta of the Adam step as checksums + a
+    strided sample.  With --check-against <file of the N=1 run> the N-GPU step must reproduce the 1-GPU step up to fp32
+    reduction order: the view-sharded gradient, summed by the one all-reduce, IS the 16-view gradient."""
+    import torch.distributed as dist
+    wl = ProductWorkload(rank, world, device, lr=1e-3)
+    wl.net.eval()
+    before = wl.opt.flat_param.clone()
+    from animatablegaussians_b200 import styleunet_ops as ops
+    with ops.step_arena():
+        items = {"smpl_pos_map": wl.d_pose, "cano2live_jnt_mats": wl.d_mats}
+        out = wl.net.render_views(items, return_depth=True, views=wl.views_dev)
+        loss = (out["rgb_maps"].sum() + out["depth_maps"].sum() + out["mask_maps"].sum()) * (1.0 / (IMG * IMG)) \
+            + (0.005 / world) * torch.linalg.norm(out["offset"], dim=-1).mean()
+        loss.backward()
+        if world > 1:
+            wl.opt.all_reduce()
+        grad = wl.opt.flat_grad.clone()
+        wl.opt.step(grad_scale=1.0, zero_grad=True)
+    loss = loss.detach().reshape(1).double()
+    if world > 1:
+        dist.all_reduce(loss)
+    torch.cuda.synchronize()
+    delta = wl.opt.flat_param - before
+    stride = 211
+    res = {"n_gpus": world, "loss": float(loss.item()), "grad_l2": float(grad.double().norm()), "grad_sum": float(grad.double().sum()),
+           "delta_l2": float(delta.double().norm()), "delta_sum": float(delta.double().sum()), "params": int(wl.opt.numel)}
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        path = os.path.join(ROOT, "gpurun_out", "check_n%d.pt" % world)
+        torch.save({"grad": grad[::stride].cpu(), "delta": delta[::stride].cpu(), "res": res}, path)
+        if args.check_against:
+            ref = torch.load(args.check_against, weights_only=False)
+            rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+            res["vs_n1"] = {"loss_rel": abs(res["loss"] - ref["res"]["loss"]) / max(abs(ref["res"]["loss"]), 1e-30),
+                            "grad_rel_l2": rel(grad[::stride].cpu(), ref["grad"]),
+                            # Adam's first step is -lr * g / (|g| + eps): entries with |g| ~ eps amplify rounding; compare
+                            # where the 1-GPU gradient is clearly non-zero
+                            "delta_rel_l2": rel(delta[::stride].cpu()[ref["grad"].abs() > 1e-6], ref["delta"][ref["grad"].abs() > 1e-6])}
+            # tolerances: fp32 summation order (atomics in the blend backward, the all-reduce tree) and, through it, a few
+            # leaky-ReLU kink / alpha-threshold flips per million gradient entries
+            res["vs_n1"]["ok"] = bool(res["vs_n1"]["loss_rel"] < 1e-5 and res["vs_n1"]["grad_rel_l2"] < 2e-3 and res["vs_n1"]["delta_rel_l2"] < 2e-2)
+        print(json.dumps({"check": res}))
+        sys.stdout.flush()
+    if world > 1:
+        _exit_multi_rank()
+    return 0 if (rank != 0 or not args.check_against or res["vs_n1"]["ok"]) else 1
+
+
 def _exit_multi_rank():
     """Leave without tearing NCCL down: the communicator is referenced by the captured CUDA graph, and
     barrier()/destroy_process_group() after a graph-captured all-reduce was observed to hang (torch 2.11 / NCCL 2.28).
@@ -241,6 +293,8 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--check", action="store_true", help="one eager step: loss / gradient / parameter-delta checksums (see run_check)")
+    ap.add_argument("--check-against", default=None, help="gpurun_out/check_n1.pt of the 1-GPU --check run to compare with")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -259,6 +313,8 @@ def main():
     torch.backends.cudnn.benchmark = True
     from animatablegaussians_b200 import _lib, stats
 
+    if args.check:
+        sys.exit(run_check(args, rank, world, device))
     wl = ProductWorkload(rank, world, device)
     if not args.no_graph:
         wl.capture()

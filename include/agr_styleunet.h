@@ -51,6 +51,15 @@ int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx
                           const float* noise, int64_t noise_period, float* d_bias, float* d_noise_w, int32_t activate,
                           void* cuda_stream);
 
+/* The reference's native op `fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)` element for element
+ * (fused_bias_act.cpp:18-31, fused_bias_act_kernel.cu:18-107), for the drop-in module dropin/fused.py:
+ *   v = x[i] + (bias ? bias[(i / step_b) % size_b] : 0);  r = refer ? refer[i] : 0
+ *   act*10+grad: 10,11 -> v | 30 -> v > 0 ? v : v*alpha | 31 -> r > 0 ? v : v*alpha | 12,32 -> 0;   out[i] = y * scale
+ * x, bias, refer, out share `dtype`; any contiguous layout (step_b = elements per bias index, size_b = bias length). */
+int agr_fused_bias_act(int32_t dtype, const void* x, const void* bias, const void* refer, void* out, int64_t size_x,
+                       int64_t step_b, int64_t size_b, int32_t act, int32_t grad, float alpha, float scale,
+                       void* cuda_stream);
+
 /* Modulated-convolution weight: w_out[co][ky][kx][ci] (KRSC, dtype) = scale*w[co][ci][ky][kx]*s[ci]*demod[co],
  * demod[co] = rsqrt(sum_{ci,k} (scale*w*s)^2 + 1e-8) if demodulate else 1.  w fp32 (Cout,Cin,k,k), s fp32 (Cin).
  * transpose_io != 0 writes w_out[ci][ky][kx][co] instead (operand of the transposed convolution).

@@ -99,9 +99,85 @@ class RefAvatar(nn.Module):
         return color, depth, alpha, offset
 
 
+def main_stock(args, rank, world, local):
+    """The reference's OWN Python through its stock code path (baseline/_ref, oracle/ref_stock.py): network/avatar.py
+    AvatarNet.render -> gaussians/gaussian_renderer.py render3 -> the reference's _C / fused / upfirdn2d extensions,
+    one pose x ONE view per iteration with torch.optim.Adam, as main_avatar.py:166-264 trains."""
+    import bench
+    from animatablegaussians_b200 import avatar as prod_avatar, synthetic as S  # synthetic data only (numpy)
+    from oracle import ref_stock
+    ref_stock.setup_paths("reference")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.manual_seed(31359)
+    torch.backends.cudnn.benchmark = True
+    P, IMG, NV, J = bench.P_GAUSS, bench.IMG, bench.N_VIEWS, bench.J
+    canonical, mats = prod_avatar.synthetic_canonical(P, size=IMG, J=J)
+    net = ref_stock.build_avatar(canonical, dev)
+    net.train()
+    extrs, Ks = S.ring_cameras(NV, img=IMG)
+    jnt = torch.from_numpy(mats).to(dev)
+    with torch.no_grad():
+        pose = net.get_pose_map({"cano2live_jnt_mats_woRoot": jnt})
+        # same emulated pre-trained state as the product arm (linear rescale of the ToRGB heads)
+        for name, style, std in (("position_net", net.position_style, 0.1), ("other_net", net.other_style, 0.3), ("color_net", net.color_style, 0.3)):
+            n = getattr(net, name)
+            m, _ = n([style], pose[:3][None], randomize_noise=False)
+            f = float(std / m.std().clamp_min(1e-12))
+            for rgbs in (n.to_rgbs1, n.to_rgbs2):
+                for t in rgbs:
+                    t.conv.weight.mul_(f); t.bias.mul_(f)
+        for rgbs in (net.other_net.to_rgbs1, net.other_net.to_rgbs2):
+            rgbs[-1].bias[0, 0] += 6.4
+    opt = torch.optim.Adam(net.parameters(), lr=1e-7)
+    views = [dict(extr=torch.from_numpy(e).to(dev), intr=torch.from_numpy(k).to(dev)) for e, k in zip(extrs, Ks)]
+
+    def step():
+        for v in range(NV):  # one reference iteration per view (batch_size 1, configs/*/avatar.yaml)
+            items = {"smpl_pos_map": pose, "cano2live_jnt_mats": jnt, "extr": views[v]["extr"], "intr": views[v]["intr"], "img_w": IMG, "img_h": IMG}
+            out = net.render(items, bg_color=(0., 0., 0.))
+            # AvatarNet.render drops the depth map (avatar.py:223-231): colour and mask only + the offset regulariser
+            loss = (out["rgb_map"].sum() + out["mask_map"].sum()) * (1.0 / (IMG * IMG)) + 0.005 * torch.linalg.norm(out["offset"], dim=-1).mean()
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+        return loss
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    sampler = bench.ClockSampler(local)
+    sampler.start()
+    ms = bench.device_time_ms(step, args.steps, 1)
+    clocks = sampler.stop()
+    ms_step = ms / args.steps
+    value = NV / (ms_step * 1e-3)
+    import diff_gaussian_rasterization_depth_alpha as D
+    import network.avatar as NA
+    out = {"impl": "reference", "metric": bench.METRIC, "value": value, "unit": "views/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": max(args.warmup, 1), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "fp32 (TF32 convs at torch defaults), as the reference", "data": "synthetic",
+           "config": {"workload": "same 16 views of one pose as the product arm, run by the reference's own code: 16 iterations of "
+                                  "AvatarNet.render (3 DualStyleUNets, LBS, render3) + loss + backward + torch.optim.Adam, batch 1, fp32",
+                      "gaussians": int(net.init_points.shape[0]), "views_per_step": NV, "image": [IMG, IMG],
+                      "code_path": "stock: %s + %s (verbatim copies in baseline/_ref); _C / fused / upfirdn2d built unmodified for sm_100a; "
+                                   "pytorch3d / plyfile stood in by oracle/shims" % (os.path.relpath(NA.__file__, ROOT), os.path.relpath(D.__file__, ROOT)),
+                      "loss": "colour + mask sums (AvatarNet.render returns no depth) + offset regulariser; the product arm also "
+                              "back-propagates a depth term"},
+           "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "cpu_baseline": {"value": value, "unit": "views/s", "cores": 0, "kind": "reference",
+                            "sample": "the reference has no CPU implementation of this path (BASELINE.json); this line is its "
+                                      "own CUDA build on 1 B200, %d steps x 16 views" % args.steps},
+           "clocks": clocks}
+    print(json.dumps(out))
+    return 0
+
+
 def main(args, rank, world, local):
     if rank != 0:
         return 0
+    from oracle import ref_stock
+    if ref_stock.available() and os.environ.get("AGR_REF_ARM", "stock") == "stock":
+        return main_stock(args, rank, world, local)
     import bench
     from animatablegaussians_b200 import avatar as prod_avatar, camera, synthetic as S  # synthetic data + camera math only
     from oracle import ref_rasterizer, styleunet_oracle as so

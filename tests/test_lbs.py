@@ -80,3 +80,64 @@ def test_skin_points_matches_oracle(built_lib):
     rx, rn = lo.skin_points(d(w), d(A), d(x), d(nrm))
     util.assert_close("pts", xo.cpu().numpy(), rx.numpy(), 1e-5)
     util.assert_close("nml", no.cpu().numpy(), rn.numpy(), 1e-5)
+
+
+def _axis_angle(axis, angle):
+    a = np.asarray(axis, np.float64); a /= np.linalg.norm(a)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * K @ K
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scaled", [False, True])
+def test_lbs_quaternion_branch_boundaries(scaled, built_lib):
+    """matrix_to_quaternion picks the best-conditioned of FOUR candidates (pytorch3d 0.7.4; restated in oracle/lbs_oracle.py —
+    PARITY UNPINNED, see its header).  Drive every candidate and the trace ~ -1 neighbourhood through the kernel:
+    one-hot skinning to joints whose rotation is the identity / 180 degrees about x, y, z (candidates 0..3 exactly),
+    the same perturbed by 1e-3 .. 0.3 rad (still one clear winner: outputs AND gradients must match), and with a
+    non-orthonormal blend (`scaled`: M = diag(1.3, 0.8, 1.1) R, where the four candidates are NOT equivalent)."""
+    from animatablegaussians_b200 import lbs
+    from oracle import lbs_oracle as lo
+    rng = np.random.default_rng(4)
+    base = [np.eye(3), _axis_angle([1, 0, 0], np.pi), _axis_angle([0, 1, 0], np.pi), _axis_angle([0, 0, 1], np.pi)]
+    mats = []
+    for R in base:
+        mats.append(R)
+        for eps in (1e-3, 1e-2, 0.3):
+            mats.append(_axis_angle(rng.normal(size=3), eps) @ R)
+    J = len(mats)
+    A = np.zeros((J, 4, 4), np.float32)
+    for j, R in enumerate(mats):
+        A[j, :3, :3] = (np.diag([1.3, 0.8, 1.1]) @ R) if scaled else R
+        A[j, :3, 3] = rng.normal(0, 0.1, 3)
+        A[j, 3, 3] = 1
+    N = J * 8
+    w = np.zeros((N, J), np.float32)
+    w[np.arange(N), np.arange(N) % J] = 1.0
+    x = rng.normal(0, 0.5, (N, 3)).astype(np.float32)
+    q = np.tile(np.array([[1, 0, 0, 0]], np.float32), (N, 1))
+    q[J:] += rng.normal(0, 0.05, (N - J, 4)).astype(np.float32)      # first J rows: exactly the identity quaternion
+    dev = "cuda"
+    tw, tA = torch.from_numpy(w).to(dev), torch.from_numpy(A).to(dev)
+    tx = torch.from_numpy(x).to(dev).requires_grad_(True)
+    tq = torch.from_numpy(q).to(dev).requires_grad_(True)
+    xo, qo = lbs.transform_cano2live(tw, tA, tx, tq)
+    gq = rng.normal(0, 1, (N, 4)).astype(np.float32)
+    qo.backward(torch.from_numpy(gq).to(dev))
+    d = lambda a: torch.from_numpy(a).double()
+    oq = d(q).requires_grad_(True)
+    rx, rq = lo.transform_cano2live(d(w), d(A), d(x), oq)
+    rq.backward(d(gq))
+    # every candidate was exercised
+    M = torch.einsum('nj,jxy->nxy', d(w), d(A))[:, :3, :3] @ lo.quaternion_to_matrix(d(q))
+    q_abs = torch.stack([1 + M[:, 0, 0] + M[:, 1, 1] + M[:, 2, 2], 1 + M[:, 0, 0] - M[:, 1, 1] - M[:, 2, 2],
+                         1 - M[:, 0, 0] + M[:, 1, 1] - M[:, 2, 2], 1 - M[:, 0, 0] - M[:, 1, 1] + M[:, 2, 2]], -1)
+    assert set(q_abs.argmax(-1).tolist()) == {0, 1, 2, 3}
+    assert float((M[:, 0, 0] + M[:, 1, 1] + M[:, 2, 2]).min()) < -0.99 + (0.3 if scaled else 0.0)
+    # rows whose winner is clear by a margin (all of them here except float ties): same branch in fp32 and fp64
+    top2 = q_abs.topk(2, dim=-1).values
+    clear = ((top2[:, 0] - top2[:, 1]) > 1e-3).numpy()
+    assert clear.mean() > 0.9
+    util.assert_close("rot", qo.detach().cpu().numpy()[clear], rq.detach().numpy()[clear], 1e-4)
+    util.assert_close("d_rot", tq.grad.cpu().numpy()[clear], oq.grad.numpy()[clear], 2e-4)
+    util.assert_close("xyz", xo.detach().cpu().numpy(), rx.numpy(), 1e-5)
