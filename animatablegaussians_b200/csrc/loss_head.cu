@@ -9,8 +9,12 @@ namespace agr {
 
 __device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 
+__device__ __forceinline__ float gtf(const float* g, int64_t i) { return g[i]; }
+__device__ __forceinline__ float gtf(const uint8_t* g, int64_t i) { return (float)g[i] * (1.f / 255.f); }   // camera images as stored
+
+template <typename GT>
 __global__ void __launch_bounds__(256) photometric_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ alpha,
-                                                              const float* __restrict__ gt_rgb, const uint8_t* __restrict__ mask,
+                                                              const GT* __restrict__ gt_rgb, const uint8_t* __restrict__ mask,
                                                               const uint8_t* __restrict__ boundary, const float* __restrict__ bg,
                                                               int64_t pixels, float g_l1, float g_mask, float* __restrict__ sums,
                                                               float* __restrict__ d_rgb, float* __restrict__ d_alpha) {
@@ -22,7 +26,7 @@ __global__ void __launch_bounds__(256) photometric_loss_kernel(const float* __re
         const bool m = mask[p] != 0;
         const float inv = 1.f - bm;
         const float r[3] = {rgb[3 * p], rgb[3 * p + 1], rgb[3 * p + 2]};
-        const float t[3] = {m ? gt_rgb[3 * p] : b0, m ? gt_rgb[3 * p + 1] : b1, m ? gt_rgb[3 * p + 2] : b2};
+        const float t[3] = {m ? gtf(gt_rgb, 3 * p) : b0, m ? gtf(gt_rgb, 3 * p + 1) : b1, m ? gtf(gt_rgb, 3 * p + 2) : b2};
         const float bgc[3] = {b0, b1, b2};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -54,16 +58,29 @@ __global__ void __launch_bounds__(256) photometric_loss_kernel(const float* __re
 
 }  // namespace agr
 
-extern "C" int agr_photometric_loss(const float* rgb, const float* alpha, const float* gt_rgb, const uint8_t* mask,
-                                    const uint8_t* boundary, const float* bg, int64_t pixels, float w_l1, float w_mask,
-                                    float* sums, float* d_rgb, float* d_alpha, void* cuda_stream) {
+template <typename GT>
+static int launch_photometric(const float* rgb, const float* alpha, const GT* gt_rgb, const uint8_t* mask, const uint8_t* boundary,
+                              const float* bg, int64_t pixels, float w_l1, float w_mask, float* sums, float* d_rgb, float* d_alpha,
+                              void* cuda_stream) {
     if (!rgb || !gt_rgb || !mask || !boundary || !bg || !sums || pixels < 0 || (d_alpha && !alpha)) return AGR_ERR_INVALID_ARGUMENT;
     if (pixels == 0) return AGR_OK;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     int64_t blocks = (pixels + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     const float g_l1 = w_l1 / (3.f * (float)pixels), g_mask = w_mask / (float)pixels;
-    agr::photometric_loss_kernel<<<(unsigned)blocks, 256, 0, s>>>(rgb, alpha, gt_rgb, mask, boundary, bg, pixels, g_l1, g_mask, sums,
-                                                                 d_rgb, d_alpha);
+    agr::photometric_loss_kernel<GT><<<(unsigned)blocks, 256, 0, s>>>(rgb, alpha, gt_rgb, mask, boundary, bg, pixels, g_l1, g_mask, sums,
+                                                                     d_rgb, d_alpha);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+extern "C" int agr_photometric_loss(const float* rgb, const float* alpha, const float* gt_rgb, const uint8_t* mask,
+                                    const uint8_t* boundary, const float* bg, int64_t pixels, float w_l1, float w_mask,
+                                    float* sums, float* d_rgb, float* d_alpha, void* cuda_stream) {
+    return launch_photometric<float>(rgb, alpha, gt_rgb, mask, boundary, bg, pixels, w_l1, w_mask, sums, d_rgb, d_alpha, cuda_stream);
+}
+
+extern "C" int agr_photometric_loss_u8(const float* rgb, const float* alpha, const uint8_t* gt_rgb, const uint8_t* mask,
+                                       const uint8_t* boundary, const float* bg, int64_t pixels, float w_l1, float w_mask,
+                                       float* sums, float* d_rgb, float* d_alpha, void* cuda_stream) {
+    return launch_photometric<uint8_t>(rgb, alpha, gt_rgb, mask, boundary, bg, pixels, w_l1, w_mask, sums, d_rgb, d_alpha, cuda_stream);
 }

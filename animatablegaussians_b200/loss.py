@@ -10,6 +10,7 @@ from . import _lib, stats
 _p = C.c_void_p
 _lib.register_symbols({
     "agr_photometric_loss": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, C.c_float, C.c_float, _p, _p, _p, _p]),
+    "agr_photometric_loss_u8": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, C.c_float, C.c_float, _p, _p, _p, _p]),
 })
 
 
@@ -19,7 +20,8 @@ class _PhotometricLoss(torch.autograd.Function):
         lib = _lib.load()
         rgb_c = rgb.detach().float().contiguous()
         alpha_c = alpha.detach().float().contiguous() if alpha is not None else None
-        gt_c = gt_rgb.detach().float().contiguous()
+        u8 = gt_rgb.dtype == torch.uint8           # camera bytes: value / 255 on the device
+        gt_c = gt_rgb.detach().contiguous() if u8 else gt_rgb.detach().float().contiguous()
         m8, b8 = mask.to(torch.uint8).contiguous(), boundary.to(torch.uint8).contiguous()
         bg_c = bg.detach().float().contiguous()
         pixels = rgb_c.numel() // 3
@@ -30,7 +32,8 @@ class _PhotometricLoss(torch.autograd.Function):
         d_alpha = torch.empty_like(alpha_c) if alpha_c is not None else None
         ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         with torch.cuda.device(rgb_c.device), stats.stage("loss_head", launches=1):
-            st = lib.agr_photometric_loss(ptr(rgb_c), ptr(alpha_c), ptr(gt_c), ptr(m8), ptr(b8), ptr(bg_c), pixels, float(w_l1),
+            fn = lib.agr_photometric_loss_u8 if u8 else lib.agr_photometric_loss
+            st = fn(ptr(rgb_c), ptr(alpha_c), ptr(gt_c), ptr(m8), ptr(b8), ptr(bg_c), pixels, float(w_l1),
                                           float(w_mask), ptr(sums), ptr(d_rgb), ptr(d_alpha),
                                           C.c_void_p(torch.cuda.current_stream(rgb_c.device).cuda_stream))
         if st != _lib.AGR_OK:
@@ -53,7 +56,7 @@ class _PhotometricLoss(torch.autograd.Function):
 
 def photometric_loss(rgb_maps, mask_maps, color_imgs, mask_imgs, boundary_mask_imgs, bg_color, w_l1=1.0, w_mask=0.1):
     """rgb_maps (V,H,W,3) / mask_maps (V,H,W,1) from `AvatarNet.render_views`, ground truth colour (V,H,W,3), boolean
-    masks (V,H,W), bg_color (3,) tensor.  Returns (w_l1 * l1 + w_mask * mask_loss, l1, mask_loss); the last two are
+    masks (V,H,W), bg_color (3,) tensor; `color_imgs` may be uint8 (the camera bytes; /255 happens in the kernel).  Returns (w_l1 * l1 + w_mask * mask_loss, l1, mask_loss); the last two are
     the per-term values the trainer logs (not differentiable)."""
     if not rgb_maps.is_cuda:
         raise RuntimeError("photometric_loss runs on the GPU only (no CPU fallback)")

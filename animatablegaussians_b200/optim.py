@@ -70,6 +70,7 @@ class FlatAdam:
         if pin:
             self._h_hyper = self._h_hyper.pin_memory()
         self._d_hyper = self._h_hyper.to(dev)
+        self._last_hyper = (float(lr), 1.0)
         self._grad_views = []
         for p, o in zip(self.params, offs):
             k = p.numel()
@@ -104,11 +105,17 @@ class FlatAdam:
         return int(self._seg_step.max().item())
 
     def refresh_hyper(self, grad_scale=None):
-        """Write lr (param_groups[0]['lr']) [and grad_scale] into the pinned pair the step's H2D copy reads.  Eager steps do
-        this themselves; call it before replaying a graph captured around step()."""
-        self._h_hyper[0] = float(self.lr)
-        if grad_scale is not None:
-            self._h_hyper[1] = float(grad_scale)
+        """Write lr (param_groups[0]['lr']) [and grad_scale] into the pinned pair the step's 8-byte H2D copy reads.  Eager
+        steps do this themselves; call it before replaying a graph captured around step().  When a value CHANGES the call
+        first waits for the device to drain: an earlier replay still in flight must read the old pair."""
+        lr = float(self.lr)
+        gs = self._last_hyper[1] if grad_scale is None else float(grad_scale)
+        if (lr, gs) != self._last_hyper:
+            if self.flat_param.is_cuda and not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream(self.flat_param.device).synchronize()
+            self._h_hyper[0] = lr
+            self._h_hyper[1] = gs
+            self._last_hyper = (lr, gs)
 
     def state_dict(self):
         """torch.optim.Adam's checkpoint layout (what the trainer stores in optm.pt, main_avatar.py:790-795): per-parameter

@@ -81,12 +81,13 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ product arm
 class ProductWorkload:
-    def __init__(self, rank, world, device, lr=1e-7):
+    def __init__(self, rank, world, device, lr=1e-7, P=P_GAUSS, n_views=N_VIEWS, dtype=torch.bfloat16):
         from animatablegaussians_b200 import avatar, optim, synthetic as S, styleunet_ops as ops
         self.rank, self.world, self.dev = rank, world, device
+        self.n_views = n_views
         torch.manual_seed(31359)
-        ops.set_compute_dtype(torch.bfloat16)
-        canonical, jnt_mats = avatar.synthetic_canonical(P_GAUSS, size=IMG, J=J)
+        ops.set_compute_dtype(dtype)
+        canonical, jnt_mats = avatar.synthetic_canonical(P, size=IMG, J=J)
         self.net = avatar.AvatarNet({"with_viewdirs": True}, canonical=canonical, device=device).to(device)
         self.net.train()
         self.P = self.net.init_points.shape[0]
@@ -94,8 +95,8 @@ class ProductWorkload:
         # random-init nets away from the emulated pre-trained state within a few steps (Gaussians grow until they fill
         # the screen), so the workload would not be stationary.  The Adam arithmetic does not depend on lr.
         self.opt = optim.FlatAdam(self.net.parameters(), lr=lr)
-        extrs, Ks = S.ring_cameras(N_VIEWS, img=IMG)
-        self.views = list(range(rank, N_VIEWS, world))
+        extrs, Ks = S.ring_cameras(n_views, img=IMG)
+        self.views = list(range(rank, n_views, world))
         self.extrs, self.Ks = [extrs[v] for v in self.views], [Ks[v] for v in self.views]
         # step inputs: host (pinned) master copies + resident device copies
         self.h_mats = torch.from_numpy(jnt_mats).pin_memory()
@@ -110,7 +111,21 @@ class ProductWorkload:
         st = self.views_dev["settings"]
         self.h_cam = torch.cat([st.viewmatrix.reshape(len(self.views), 16), st.projmatrix.reshape(len(self.views), 16),
                                 st.campos], 1).cpu().pin_memory()
-        self.h2d_bytes = self.h_mats.numel() * 4 + self.h_pose.numel() * 4 + self.h_cam.numel() * 4
+        # ground truth of this rank's views as the cameras store it: uint8 colour + boolean mask + boundary band
+        # (main_avatar.py:193-222 reads color_img / mask_img / boundary_mask_img); synthesised from the initial render
+        import torch.nn.functional as F
+        with torch.no_grad():
+            out = self.net.render_views({"smpl_pos_map": self.d_pose, "cano2live_jnt_mats": self.d_mats}, views=self.views_dev)
+            m = (out["mask_maps"][..., 0] > 0.5)
+            mf = m.float()[:, None]
+            band = (F.max_pool2d(mf, 5, 1, 2) - (1.0 - F.max_pool2d(1.0 - mf, 5, 1, 2)))[:, 0] > 0
+            gt = (out["rgb_maps"].clamp(0, 1) * 0.7 + 0.15).mul(255.0).round().to(torch.uint8)
+        self.h_gt, self.h_mask, self.h_band = gt.cpu().pin_memory(), m.to(torch.uint8).cpu().pin_memory(), band.to(torch.uint8).cpu().pin_memory()
+        self.d_gt, self.d_mask, self.d_band = gt.contiguous(), m.to(torch.uint8).contiguous(), band.to(torch.uint8).contiguous()
+        self.bg = torch.zeros(3, device=device)
+        del out
+        self.h2d_bytes = (self.h_mats.numel() * 4 + self.h_pose.numel() * 4 + self.h_cam.numel() * 4 + self.h_gt.numel()
+                          + self.h_mask.numel() + self.h_band.numel())
         self.d2h_bytes = 4
         self.graph = None
 
@@ -119,17 +134,23 @@ class ProductWorkload:
         with ops.step_arena():
             return self._body_impl()
 
+    def _loss(self, out):
+        """Loss head of the trainer on the device (main_avatar.py:193-222: boundary compositing, L1 image, L1 mask; one fused
+        kernel, include/agr_loss.h) + a small depth sum so that colour, depth AND alpha all receive gradients (SURVEY.md
+        §8d config 4) + the offset regulariser.  Photometric terms are means over this rank's views (weighted by the rank's
+        share), the view-independent regulariser is split over the ranks: the summed gradient is the 1-GPU gradient."""
+        from animatablegaussians_b200 import loss as L
+        photo, _, _ = L.photometric_loss(out["rgb_maps"], out["mask_maps"], self.d_gt, self.d_mask, self.d_band, self.bg, w_l1=1.0, w_mask=0.1)
+        return photo * (len(self.views) / float(self.n_views)) + out["depth_maps"].sum() * (1e-3 / (IMG * IMG * self.n_views)) \
+            + (0.005 / self.world) * torch.linalg.norm(out["offset"], dim=-1).mean()
+
     def _body_impl(self):
         items = {"smpl_pos_map": self.d_pose, "cano2live_jnt_mats": self.d_mats}
-        out = self.net.render_views(items, return_depth=True, views=self.views_dev)
-        # plain sums so that colour, depth AND alpha receive gradients + offset regulariser
-        # (the view-independent regulariser is split over the ranks: the summed gradient is the 1-GPU gradient)
-        loss = (out["rgb_maps"].sum() + out["depth_maps"].sum() + out["mask_maps"].sum()) * (1.0 / (IMG * IMG)) \
-            + (0.005 / self.world) * torch.linalg.norm(out["offset"], dim=-1).mean()
+        loss = self._loss(self.net.render_views(items, return_depth=True, views=self.views_dev))
         loss.backward()
         if self.world > 1:
             self.opt.all_reduce()
-        self.opt.step(grad_scale=1.0, zero_grad=True, graph_safe=True)
+        self.opt.step(grad_scale=1.0, zero_grad=True)
         return loss.detach().reshape(1)
 
     def capture(self):
@@ -160,15 +181,44 @@ class ProductWorkload:
             raise RuntimeError("sync-free rasterizer: binning capacity exceeded (%d instances)" % int(st[0].item()))
         return None if st is None else int(st[0].item())
 
+    def _e2e_setup(self):
+        st = self.views_dev["settings"]
+        V = len(self.views)
+        self._host_inputs = [self.h_mats, self.h_pose, self.h_cam, self.h_gt, self.h_mask, self.h_band]
+        self._staging = [torch.empty_like(h, device=self.dev) for h in self._host_inputs]
+
+        def consume():   # staging -> the graph's static input tensors (device-to-device, ~90 MB at HBM rate)
+            m, p, c, g, k, b = self._staging
+            self.d_mats.copy_(m); self.d_pose.copy_(p)
+            st.viewmatrix.copy_(c[:, :16].reshape(V, 4, 4)); st.projmatrix.copy_(c[:, 16:32].reshape(V, 4, 4)); st.campos.copy_(c[:, 32:35])
+            self.d_gt.copy_(g); self.d_mask.copy_(k); self.d_band.copy_(b)
+        self._consume = consume
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self._staged, self._staging_free = torch.cuda.Event(), torch.cuda.Event()
+        self._staging_free.record(torch.cuda.current_stream())
+        self._upload_pending = False
+
+    def _upload(self):
+        """This step's inputs (pose map, joint matrices, cameras, 16 ground-truth images + masks as bytes) from pinned host
+        memory into device staging buffers on a copy stream: the upload of step i+1 overlaps the compute of step i."""
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._staging_free)
+            for d, h in zip(self._staging, self._host_inputs):
+                d.copy_(h, non_blocking=True)
+            self._staged.record(self.copy_stream)
+        self._upload_pending = True
+
     def step(self, e2e):
-        if e2e:  # this step's inputs come from pinned host memory
-            st = self.views_dev["settings"]
-            V = len(self.views)
-            self.d_mats.copy_(self.h_mats, non_blocking=True)
-            self.d_pose.copy_(self.h_pose, non_blocking=True)
-            st.viewmatrix.copy_(self.h_cam[:, :16].reshape(V, 4, 4), non_blocking=True)
-            st.projmatrix.copy_(self.h_cam[:, 16:32].reshape(V, 4, 4), non_blocking=True)
-            st.campos.copy_(self.h_cam[:, 32:35], non_blocking=True)
+        if e2e:  # this step's inputs come from pinned host memory (one upload per step, pipelined one step ahead)
+            if getattr(self, "copy_stream", None) is None:
+                self._e2e_setup()
+            if not self._upload_pending:
+                self._upload()
+            main = torch.cuda.current_stream()
+            main.wait_event(self._staged)
+            self._consume()
+            self._staging_free.record(main)
+            self._upload()
         if self.graph is not None:
             self.opt.refresh_hyper()       # lr schedule: the captured step re-reads the pinned {lr, grad_scale} pair
             self.graph.replay()
@@ -238,9 +288,7 @@ def run_check(args, rank, world, device):
     from animatablegaussians_b200 import styleunet_ops as ops
     with ops.step_arena():
         items = {"smpl_pos_map": wl.d_pose, "cano2live_jnt_mats": wl.d_mats}
-        out = wl.net.render_views(items, return_depth=True, views=wl.views_dev)
-        loss = (out["rgb_maps"].sum() + out["depth_maps"].sum() + out["mask_maps"].sum()) * (1.0 / (IMG * IMG)) \
-            + (0.005 / world) * torch.linalg.norm(out["offset"], dim=-1).mean()
+        loss = wl._loss(wl.net.render_views(items, return_depth=True, views=wl.views_dev))
         loss.backward()
         if world > 1:
             wl.opt.all_reduce()
@@ -276,6 +324,124 @@ def run_check(args, rank, world, device):
     return 0 if (rank != 0 or not args.check_against or res["vs_n1"]["ok"]) else 1
 
 
+def _time_ms(fn, steps, warmup):
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_aux_config(args, device):
+    """BASELINE.json configs other than the headline (1-based): 1 smplx LBS of 10k vertices, 2 single-view forward raster of
+    300k Gaussians, 3 full forward (StyleUNet -> LBS -> raster) of 4 views in fp32.  One GPU, one JSON line each."""
+    from animatablegaussians_b200 import avatar, camera, synthetic as S, styleunet_ops as ops
+    sampler = ClockSampler(device.index or 0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    base = {"n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "data": "synthetic"}
+    if args.config == 2:
+        import diff_gaussian_rasterization_depth_alpha as D   # the drop-in surface, as gaussian_renderer.py:14 imports it
+        g = S.make_gaussians(P_GAUSS)
+        extrs, Ks = S.ring_cameras(N_VIEWS, img=IMG)
+        host = {k: torch.from_numpy(g[k]).pin_memory() for k in ("xyz", "opacity", "scales", "rotations", "rgb")}
+        dev = {k: v.to(device) for k, v in host.items()}
+        rs = camera.make_raster_settings(extrs[0], Ks[0], IMG, IMG, torch.zeros(3, device=device), device)
+        rast = D.GaussianRasterizer(rs)
+        h_out = torch.zeros(1).pin_memory()
+
+        def step(e2e=False):
+            if e2e:
+                for k in dev:
+                    dev[k].copy_(host[k], non_blocking=True)
+            with torch.no_grad():
+                color, radii, depth, alpha = rast(means3D=dev["xyz"], means2D=torch.zeros_like(dev["xyz"]), opacities=dev["opacity"],
+                                                  colors_precomp=dev["rgb"], scales=dev["scales"], rotations=dev["rotations"])
+                if e2e:
+                    h_out.copy_(color.sum().reshape(1), non_blocking=True)
+        sampler.start()
+        ms = _time_ms(step, args.steps, args.warmup)
+        ms_e2e = _time_ms(lambda: step(True), args.steps, 3)
+        clocks = sampler.stop()
+        bytes_fwd = 60.0 * P_GAUSS + 24.0 * IMG * IMG     # SURVEY §8d forward terms: 56 B/Gaussian in + 4 B radii + 24 B/pixel out
+        out = dict(base, metric="rendered views/sec, forward raster only @300k Gaussians, 1024x1024, 1 view per call", value=1e3 / ms,
+                   unit="views/s", ms_per_step=ms, dtype="fp32",
+                   config={"workload": "BASELINE configs[1]: single-view forward raster of 300k posed Gaussians through "
+                                       "diff_gaussian_rasterization_depth_alpha.GaussianRasterizer (colours precomputed, one view per call, "
+                                       "blocking instance-count read as in the reference API)", "gaussians": P_GAUSS, "image": [IMG, IMG]},
+                   e2e={"value": 1e3 / ms_e2e, "unit": "views/s", "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "d2h_bytes_per_step": 4},
+                   gpu_launches=None, clocks=clocks,
+                   roofline={"bound": "hbm", "kernel": "forward rasterizer launches of one view", "achieved": bytes_fwd / (ms * 1e-3) / 1e9, "peak": hbm,
+                             "unit": "GB/s", "frac": bytes_fwd / (ms * 1e-3) / 1e9 / hbm, "traffic": None, "algorithmic_bytes_per_step": bytes_fwd})
+    elif args.config == 3:
+        ops.set_compute_dtype(torch.float32)
+        torch.manual_seed(31359)
+        V = 4
+        canonical, mats = avatar.synthetic_canonical(P_GAUSS, size=IMG, J=J)
+        net = avatar.AvatarNet({"with_viewdirs": True}, canonical=canonical, device=device).to(device).eval()
+        extrs, Ks = S.ring_cameras(N_VIEWS, img=IMG)
+        h_mats = torch.from_numpy(mats).pin_memory()
+        d_mats = h_mats.to(device)
+        with torch.no_grad():
+            pose = net.get_pose_map({"cano2live_jnt_mats_woRoot": d_mats})
+            avatar.emulate_pretrained_heads(net, pose[:3])
+        h_pose = pose.cpu().pin_memory()
+        views = net.prepare_views(extrs[:V], Ks[:V], IMG, IMG)
+        h_out = torch.zeros(1).pin_memory()
+
+        def step(e2e=False):
+            if e2e:
+                d_mats.copy_(h_mats, non_blocking=True)
+                pose.copy_(h_pose, non_blocking=True)
+            with torch.no_grad():
+                out = net.render_views({"smpl_pos_map": pose, "cano2live_jnt_mats": d_mats}, views=views)
+                if e2e:
+                    h_out.copy_(out["rgb_maps"].sum().reshape(1), non_blocking=True)
+        sampler.start()
+        ms = _time_ms(step, args.steps, args.warmup)
+        ms_e2e = _time_ms(lambda: step(True), args.steps, 3)
+        clocks = sampler.stop()
+        out = dict(base, metric="rendered views/sec, full forward (StyleUNet -> LBS -> raster), 4 views @1024x1024, fp32", value=V * 1e3 / ms,
+                   unit="views/s", ms_per_step=ms, dtype="fp32 (exact: CUDA-core convolutions, no TF32)",
+                   config={"workload": "BASELINE configs[2]: AvatarNet.render_views, 4 views of one pose, eval mode, fp32 compute",
+                           "gaussians": int(net.init_points.shape[0]), "views_per_step": V, "image": [IMG, IMG]},
+                   e2e={"value": V * 1e3 / ms_e2e, "unit": "views/s", "h2d_bytes_per_step": h_mats.numel() * 4 + h_pose.numel() * 4, "d2h_bytes_per_step": 4},
+                   gpu_launches=None, clocks=clocks,
+                   roofline={"bound": "tensor", "kernel": "fp32 parity path: CUDA-core implicit-GEMM convolutions (conv_direct_kernel)", "achieved": (3 * 585.8e9 + (V - 1) * 136.0e9) / (ms * 1e-3) / 1e12,
+                             "peak": 80.0, "unit": "TFLOP/s", "frac": (3 * 585.8e9 + (V - 1) * 136.0e9) / (ms * 1e-3) / 1e12 / 80.0, "traffic": None,
+                             "peak_source": "nominal fp32 FMA rate of B200 (148 SMs x 128 lanes x 2 x 1.965 GHz ~ 74-80 TFLOP/s): this path does not use tensor cores"})
+        ops.set_compute_dtype(torch.float32)
+    else:   # config 1
+        from animatablegaussians_b200 import smpl_lbs
+        rng = np.random.default_rng(0)
+        Vn, Jn, NB = 10000, 55, 20
+        t = lambda a: torch.from_numpy(np.asarray(a, np.float32)).to(device)
+        parents = np.arange(-1, Jn - 1); parents[0] = -1
+        model = dict(betas=t(rng.normal(0, 1, (1, NB))), pose=t(rng.normal(0, 0.2, (1, Jn * 3))), v_template=t(rng.normal(0, 0.5, (Vn, 3))),
+                     shapedirs=t(rng.normal(0, 0.01, (Vn, 3, NB))), posedirs=t(rng.normal(0, 0.01, ((Jn - 1) * 9, Vn * 3))),
+                     J_regressor=t(np.abs(rng.normal(0, 1, (Jn, Vn))) / Vn), parents=torch.from_numpy(parents).to(device),
+                     lbs_weights=t(rng.dirichlet(np.ones(Jn) * 0.1, Vn)))
+        sampler.start()
+        ms = _time_ms(lambda: smpl_lbs.lbs(**model, return_affine_mat=True), args.steps, args.warmup)
+        clocks = sampler.stop()
+        out = dict(base, metric="smplx.lbs.lbs calls/sec, 10k vertices, 55 joints", value=1e3 / ms, unit="calls/s", ms_per_step=ms, dtype="fp32",
+                   config={"workload": "BASELINE configs[0]: SMPL-X linear blend skinning of 10k vertices (plumbing check; the reference runs it on the CPU)"},
+                   e2e={"value": 1e3 / ms, "unit": "calls/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=None, clocks=clocks,
+                   roofline={"bound": "hbm", "kernel": "agr_lbs_points + agr_smpl_joint_chain (latency-bound at this size)", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None, "traffic": None})
+    print(json.dumps(out))
+    return 0
+
+
 def _exit_multi_rank():
     """Leave without tearing NCCL down: the communicator is referenced by the captured CUDA graph, and
     barrier()/destroy_process_group() after a graph-captured all-reduce was observed to hang (torch 2.11 / NCCL 2.28).
@@ -293,6 +459,8 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json configs, 1-based: 4 = the headline train step (default), 5 = 500k Gaussians x 24 views; 1-3: auxiliary lines")
     ap.add_argument("--check", action="store_true", help="one eager step: loss / gradient / parameter-delta checksums (see run_check)")
     ap.add_argument("--check-against", default=None, help="gpurun_out/check_n1.pt of the 1-GPU --check run to compare with")
     args = ap.parse_args()
@@ -315,7 +483,14 @@ def main():
 
     if args.check:
         sys.exit(run_check(args, rank, world, device))
-    wl = ProductWorkload(rank, world, device)
+    if args.config in (1, 2, 3):
+        if rank == 0:
+            run_aux_config(args, device)
+        if world > 1:
+            _exit_multi_rank()
+        return
+    n_views, n_gauss = (24, 500000) if args.config == 5 else (N_VIEWS, P_GAUSS)
+    wl = ProductWorkload(rank, world, device, P=n_gauss, n_views=n_views)
     if not args.no_graph:
         wl.capture()
     for _ in range(args.warmup):
@@ -356,8 +531,8 @@ def main():
         for lab, (t, n) in sorted(st["detail"].items(), key=lambda kv: -kv[1][0]):
             print("%-46s n/step %5.1f  ms/step %8.4f" % (lab, n / args.steps, t / args.steps), file=sys.stderr)
     ms_step = ms / args.steps
-    value = N_VIEWS / (ms_step * 1e-3)
-    e2e_value = N_VIEWS / (ms_e2e / args.steps * 1e-3)
+    value = n_views / (ms_step * 1e-3)
+    e2e_value = n_views / (ms_e2e / args.steps * 1e-3)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -366,12 +541,13 @@ def main():
     roof = stats.roofline(st, args.steps, len(wl.views), wl.P, IMG, IMG, peaks)
     roof_tc = stats.roofline_tensor(st, args.steps, peaks)
     out = {
-        "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if args.config == 4 else "rendered views/sec fwd+bwd @500k Gaussians, 1024x1024, 24 cams", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16 (StyleUNet) + fp32 (LBS, rasterizer)", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[3]: train step fwd+bwd+Adam, synthetic 300k-Gaussian capsule avatar, "
-                               "1 pose x 16 views @1024x1024, bf16 StyleUNet, view-sharded over %d GPU(s)" % world,
-                   "gaussians": wl.P, "views_per_step": N_VIEWS, "views_per_rank": len(wl.views), "image": [IMG, IMG],
+        "config": {"workload": "BASELINE configs[%d]: train step fwd+bwd+Adam (loss head on the device: L1 image + L1 mask vs uint8 ground truth, "
+                               "depth term, offset regulariser), synthetic %dk-Gaussian capsule avatar, 1 pose x %d views @1024x1024, "
+                               "bf16 StyleUNet, view-sharded over %d GPU(s)" % (args.config - 1, wl.P // 1000, n_views, world),
+                   "gaussians": wl.P, "views_per_step": n_views, "views_per_rank": len(wl.views), "image": [IMG, IMG],
                    "parallelism": "view-shard x%d + 1 all-reduce" % world, "cuda_graph": not args.no_graph,
                    "tile_instances_per_step": instances,
                    "l2": "step working set (activations, maps, instance streams: several GB) exceeds the 126 MB L2; no explicit flush",

@@ -30,6 +30,11 @@ extern "C" {
 int agr_photometric_loss(const float* rgb, const float* alpha, const float* gt_rgb, const uint8_t* mask,
                          const uint8_t* boundary, const float* bg, int64_t pixels, float w_l1, float w_mask,
                          float* sums, float* d_rgb, float* d_alpha, void* cuda_stream);
+/* Same, with the ground-truth colour as the camera stores it: gt_rgb (pixels,3) uint8, value / 255 (the dataset divides by
+ * 255 on the host, dataset/dataset_mv_rgb.py; uploading bytes quarters the H2D traffic of a 16-view step). */
+int agr_photometric_loss_u8(const float* rgb, const float* alpha, const uint8_t* gt_rgb, const uint8_t* mask,
+                            const uint8_t* boundary, const float* bg, int64_t pixels, float w_l1, float w_mask,
+                            float* sums, float* d_rgb, float* d_alpha, void* cuda_stream);
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,7 @@ def test_captured_graph_follows_the_lr_schedule(built_lib):
         body(b, opt)
     body(a, ref); ref.zero_grad()                        # the captured step itself does not execute: replay below
     graph.replay()
+    torch.cuda.synchronize()
     for it in range(5):
         lr = 1e-3 * (0.5 ** (it + 1))
         for grp in ref.param_groups:

@@ -115,8 +115,12 @@ def test_avatar_render_matches_stock_reference(built_lib, tmp_path):
         assert _l2(get("mask_map"), a["mask_map"]) <= 1e-3, name + ":mask_map rel L2 %.3e" % _l2(get("mask_map"), a["mask_map"])
         util.assert_close_robust(name + ":rgb_map", get("rgb_map"), a["rgb_map"], 2e-3, outlier_frac=5e-3, outlier_tol=1e-1)
         util.assert_close_robust(name + ":mask_map", get("mask_map"), a["mask_map"], 2e-3, outlier_frac=5e-3, outlier_tol=1e-1)
+        errs = {}
         for k in ref_stock.GRAD_KEYS:
             gk = other["grad:" + k] if other is not None else named[k].grad.detach().cpu().numpy()
-            # whole-network gradients cross ~40 leaky-ReLU kinks -> relative L2 (see tests/test_styleunet.py::_check)
-            assert _l2(gk, a["grad:" + k]) <= 2e-2, "%s: grad %s rel L2 %.3e" % (name, k, _l2(gk, a["grad:" + k]))
+            errs[k] = _l2(gk, a["grad:" + k])
+        print(name, "parameter-gradient rel L2 vs the stock reference:", {k: "%.2e" % v for k, v in errs.items()})
+        # whole-network gradients cross ~40 leaky-ReLU kinks -> relative L2 (see tests/test_styleunet.py::_check)
+        bad = {k: v for k, v in errs.items() if v > 2e-2}
+        assert not bad, "%s: %s" % (name, {k: "%.3e" % v for k, v in bad.items()})
     ops.set_compute_dtype(torch.float32)
