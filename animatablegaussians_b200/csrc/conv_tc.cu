@@ -374,7 +374,11 @@ bool forward_supported(const AgrConvGeom& g) {
     return build_taps(g, &t, &is, &os, &GH, &GW);
 }
 
+int conv_tc_generation();
+int launch_forward_v2(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, cudaStream_t s);
+
 int launch_forward(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, cudaStream_t s) {
+    if (conv_tc_generation() >= 2) return launch_forward_v2(g, x, w, y, ep, s);   // conv_tc2.cu: tap groups + CTA pairs
     ConvParams p;
     if (!forward_supported(g) || !build_taps(g, &p.taps, &p.in_stride, &p.out_stride, &p.GH, &p.GW)) return AGR_ERR_INVALID_ARGUMENT;
     const int cin_total = ep.w_cin_total > 0 ? ep.w_cin_total : g.Cin;
@@ -395,6 +399,8 @@ int launch_forward(const AgrConvGeom& g, const void* x, const void* w, void* y, 
     if (ctas <= 148) return launch_s<128, 4>(mx, mw, p, s);
     return launch_s<128, 3>(mx, mw, p, s);
 }
+
+static int g_wgrad_ctas = 2 * 148;
 
 bool wgrad_supported(const AgrConvGeom& g) {
     if (!geom_ok(g)) return false;
@@ -450,7 +456,7 @@ int launch_wgrad(const AgrConvGeom& g, const void* x, const void* dy, float* dw,
     p.stages = stages;
     const long boxes = (long)g.N * ((p.GH + TILE_H - 1) / TILE_H) * ((p.GW + TILE_W - 1) / TILE_W);
     const long tiles = (long)(g.Cin / MT) * (g.Cout / NT) * ng;
-    long slices = (2 * 148 + tiles - 1) / tiles;            // ~2 waves of CTAs (1 CTA / SM), each with >= 2 pixel boxes when possible
+    long slices = (g_wgrad_ctas + tiles - 1) / tiles;       // ~2 waves of CTAs (1 CTA / SM), each with >= 2 pixel boxes when possible
     if (slices > boxes / 2) slices = boxes / 2;
     if (slices < 1) slices = 1;
     p.slices = (int)slices;
@@ -466,3 +472,8 @@ int launch_wgrad(const AgrConvGeom& g, const void* x, const void* dy, float* dw,
 
 }  // namespace tc
 }  // namespace agr
+
+extern "C" int agr_conv2d_set_wgrad_ctas(int32_t ctas) {
+    if (ctas > 0) agr::tc::g_wgrad_ctas = ctas;
+    return agr::tc::g_wgrad_ctas;
+}

@@ -784,6 +784,8 @@ _lib.register_symbols({
     "agr_conv2d_dgrad": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), _p, _p, _p, _p]),
     "agr_conv2d_wgrad": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), _p, _p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
     "agr_weight_transpose": (C.c_int, [C.c_int32, _p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
+    "agr_conv2d_set_generation": (C.c_int, [C.c_int32]),
+    "agr_conv2d_set_wgrad_ctas": (C.c_int, [C.c_int32]),
 })
 
 _STAGE = {1: "styleunet_conv_tc", 2: "styleunet_conv_direct"}

@@ -73,6 +73,13 @@ int agr_conv2d_wgrad(int32_t dtype, const AgrConvGeom* g, const void* x, const v
 /* w_out[ci][t][co] = w_krsc[co][t][ci]  (dtype elements). */
 int agr_weight_transpose(int32_t dtype, const void* w_krsc, void* w_out, int32_t Cout, int32_t Cin, int32_t ksize,
                          void* cuda_stream);
+/* Tuning / A-B switch of path 1's forward-form kernel (same results, different staging): 1 = one TMA box per tap
+ * (conv_tc_kernel), 2 = tap groups sharing one haloed box, 3 = tap groups + CTA pairs (cta_group::2; the default, also
+ * selectable with the environment variable AGR_CONV_TC).  Returns the generation now in force; 0 leaves it unchanged. */
+int agr_conv2d_set_generation(int32_t generation);
+/* Tuning: number of CTAs path 1's weight-gradient kernel aims for when it splits the pixel range (split-K with fp32
+ * reductions into dw; more CTAs = more parallelism but more reduction traffic).  Returns the value in force; <= 0 leaves it. */
+int agr_conv2d_set_wgrad_ctas(int32_t ctas);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,9 @@ GRAD_KEYS = ("position_net.convs1.1.conv.weight", "position_net.to_rgbs2.5.conv.
              "viewdir_net.0.weight", "viewdir_net.2.weight", "viewdir_net.2.bias")
 
 
+PG_KEYS = ("positions", "opacity", "scales", "rotations", "colors")
+
+
 def case_avatar(z, dev, state):
     """AvatarNet.render (network/avatar.py:161-239) in eval mode (no view-direction noise), loss on rgb / mask / offset."""
     import torch
@@ -119,6 +122,9 @@ def case_avatar(z, dev, state):
     items = {"smpl_pos_map": _t(z, "smpl_pos_map", dev).float(), "cano2live_jnt_mats": _t(z, "jnt_mats", dev).float(),
              "extr": _t(z, "extr", dev).float(), "intr": _t(z, "intr", dev).float(), "img_w": int(z["W"]), "img_h": int(z["H"])}
     out = net.render(items, bg_color=(0., 0., 0.))
+    pg = out["posed_gaussians"]          # eval mode returns the posed Gaussians handed to render3 (network/avatar.py:233-237)
+    for k in PG_KEYS:
+        pg[k].retain_grad()
     loss = (out["rgb_map"] * _t(z, "g_rgb", dev)).sum() + (out["mask_map"] * _t(z, "g_mask", dev)).sum() + (out["offset"] * _t(z, "g_offset", dev)).sum()
     loss.backward()
     named = dict(net.named_parameters())
@@ -127,6 +133,8 @@ def case_avatar(z, dev, state):
            "n_state": torch.tensor([len(net.state_dict())]), "missing": torch.tensor([len(missing.missing_keys) + len(missing.unexpected_keys)])}
     for k in GRAD_KEYS:
         res["grad:" + k] = named[k].grad
+    for k in PG_KEYS:                    # the rasterizer's inputs and the gradients it returned for them
+        res["pg:" + k], res["dpg:" + k] = pg[k], pg[k].grad
     return {k: v.detach().float().cpu().numpy() for k, v in res.items()}
 
 

@@ -80,6 +80,9 @@ GROUPS = {
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if len(sys.argv) > 2:     # generation of the forward-form tcgen05 kernel (include/agr_conv.h agr_conv2d_set_generation)
+        from animatablegaussians_b200 import _lib
+        print("generation", _lib.load().agr_conv2d_set_generation(int(sys.argv[2])), flush=True)
     ok = True
     for name, cases in GROUPS.items():
         if which not in ("all", name):
