@@ -116,9 +116,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // Instruction descriptor (InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10, a_major @15, b_major @16
 // (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24.
-__device__ __forceinline__ uint32_t umma_idesc(int M, int N, int mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(mn_major ? 3 : 0) << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc2(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N, int mn_major) { return umma_idesc2(M, N, mn_major, mn_major); }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

@@ -726,7 +726,7 @@ int launch_transpose(int dtype, const void* in, void* out, int Cout, int Cin, in
 namespace agr {
 namespace tc {
 bool forward_supported(const AgrConvGeom& g);
-int launch_forward(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, cudaStream_t s);
+int launch_forward(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, bool w_mn, cudaStream_t s);
 bool wgrad_supported(const AgrConvGeom& g);
 int launch_wgrad(const AgrConvGeom& g, const void* x, const void* dy, float* dw, int ci_total, int ci_offset, cudaStream_t s);
 }  // namespace tc
@@ -754,9 +754,20 @@ int agr_conv2d_forward(int32_t dtype, const AgrConvGeom* g, const void* x, const
     if (ep) e = *ep;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     const int path = agr_conv2d_path(dtype, g, 0);
-    if (path == 1) return tc::launch_forward(*g, x, w_krsc, y, e, s);
+    if (path == 1) return tc::launch_forward(*g, x, w_krsc, y, e, false, s);
     if (path == 2) return direct::launch_forward(dtype, *g, x, w_krsc, y, e, s);
     return AGR_ERR_INVALID_ARGUMENT;
+}
+
+int agr_conv2d_dgrad_krsc(int32_t dtype, const AgrConvGeom* g, const void* dy, const void* w_krsc, int32_t w_cin_total, int32_t w_cin_offset,
+                          void* dx, void* cuda_stream) {
+    using namespace agr;
+    if (!g || !dy || !w_krsc || !dx || !tc::geom_ok(*g)) return AGR_ERR_INVALID_ARGUMENT;
+    if (agr_conv2d_path(dtype, g, 1) != 1) return AGR_ERR_INVALID_ARGUMENT;   // path 2 contracts with the transposed operand
+    const AgrConvGeom a = tc::adjoint(*g);
+    AgrConvEpilogue e{};
+    e.w_cin_total = w_cin_total; e.w_cin_offset = w_cin_offset;
+    return tc::launch_forward(a, dy, w_krsc, dx, e, true, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int agr_conv2d_dgrad(int32_t dtype, const AgrConvGeom* g, const void* dy, const void* w_t, void* dx, void* cuda_stream) {

@@ -50,7 +50,11 @@ struct ConvParams {
     int activate;           // 0 | 1 lrelu*sqrt2 | 2 lrelu
 };
 
-template <int BN, int STAGES>
+// B_MN: the weight operand is read straight from the KRSC tensor of the layer whose DATA GRADIENT this launch computes
+// (w[co][tap][ci]: the contraction index co is the slow one), i.e. as an MN-major B operand: boxes {64 ci, 1 tap, 64 co}
+// land as 64 K-rows of 128 B, N atoms of 64 ci are LBO = 8 KB apart, a K step of 16 rows is +2048 B — the layout the
+// weight-gradient kernel below uses for both of its operands.  No transposed copy of the weight exists.
+template <int BN, int STAGES, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, (STAGES * (A_BYTES + BN * BK * 2) + 1024) * 2 <= MAX_SMEM ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ ConvParams p) {
     constexpr int B_BYTES = BN * BK * 2;
@@ -99,13 +103,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 // OOB -> zeros = padding; with in_stride 2 the box holds every other pixel from its origin
                 tma_load_4d(a_dst, &map_x, &full_bar[s], ck * BK, p.in_stride * w0 + p.taps.dx[tap], p.in_stride * h0 + p.taps.dy[tap], img);
-                tma_load_3d(b_dst, &map_w, &full_bar[s], p.w_cin_offset + ck * BK, p.taps.wt[tap], n0);
+                if (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_3d(b_dst + j * (64 * BK * 2), &map_w, &full_bar[s], p.w_cin_offset + n0 + 64 * j, p.taps.wt[tap], ck * BK);
+                } else {
+                    tma_load_3d(b_dst, &map_w, &full_bar[s], p.w_cin_offset + ck * BK, p.taps.wt[tap], n0);
+                }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one elected lane) =================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc(BM, BN, 0);
+            const uint32_t idesc = umma_idesc2(BM, BN, 0, B_MN ? 1 : 0);
             for (int it = 0; it < num_kb; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -113,10 +123,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t b_addr = a_addr + A_BYTES;
-                const uint64_t adesc = umma_desc(a_addr, 16), bdesc = umma_desc(b_addr, 16);
+                const uint64_t adesc = umma_desc(a_addr, 16), bdesc = umma_desc(b_addr, B_MN ? 64 * BK * 2 : 16);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 B -> +2 in the (>>4) start-address field
-                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16: +32 B along a K-major row, +16 rows (2048 B) of an MN-major tile
+                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc, (it | k) != 0 ? 1u : 0u);
                 umma_commit(&empty_bar[s]);      // frees the smem stage once these MMAs have read it
             }
             umma_commit(&tmem_full_bar);         // accumulator complete
@@ -221,11 +231,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int tiles_w = (p.GW + TILE_W - 1) / TILE_W, tiles_h = (p.GH + TILE_H - 1) / TILE_H;
     const int boxes_img = tiles_w * tiles_h;
     const long total_boxes = (long)p.N * boxes_img;
-    const int box0 = (int)((blockIdx.x * total_boxes) / p.slices), box1 = (int)(((blockIdx.x + 1) * total_boxes) / p.slices);
+    // grid = (tap groups, channel tiles, pixel slices): CTAs that read the SAME pixel boxes are neighbours in launch order, so
+    // the operands of a slice come from HBM once and from L2 for the other groups / tiles
+    const int box0 = (int)((blockIdx.z * total_boxes) / p.slices), box1 = (int)(((blockIdx.z + 1) * total_boxes) / p.slices);
     const int num_kb = box1 - box0;                        // host keeps slices <= total_boxes
     const int n_tiles = p.Cout / NT;
     const int ci0 = (blockIdx.y / n_tiles) * MT, co0 = (blockIdx.y % n_tiles) * NT;
-    const WgradGroup grp = p.groups[blockIdx.z];
+    const WgradGroup grp = p.groups[blockIdx.x];
     const int a_box = p.rows_x * ROW_BYTES, b_box = p.rows_y * ROW_BYTES;     // one 64-channel box of each operand
     const int a_bytes = (MT / 64) * a_box, stage_bytes = a_bytes + (NT / 64) * b_box;
     const int STAGES = p.stages;
@@ -354,16 +366,16 @@ static bool make_map_w(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool B_MN>
 static int launch_s(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, cudaStream_t s) {
     constexpr int smem = STAGES * (A_BYTES + BN * BK * 2) + 1024;
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
+        if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
         attr = true;
     }
     dim3 grid(p.N * ((p.GH + TILE_H - 1) / TILE_H) * ((p.GW + TILE_W - 1) / TILE_W), p.Cout / BN, p.taps.n_phase);
-    conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, s>>>(mx, mw, p);
+    conv_tc_kernel<BN, STAGES, B_MN><<<grid, NUM_THREADS, smem, s>>>(mx, mw, p);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 
@@ -375,14 +387,19 @@ bool forward_supported(const AgrConvGeom& g) {
 }
 
 int conv_tc_generation();
-int launch_forward_v2(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, cudaStream_t s);
+bool use_v2(const AgrConvGeom& g);
+int launch_forward_v2(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, bool w_mn, cudaStream_t s);
 
-int launch_forward(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, cudaStream_t s) {
-    if (conv_tc_generation() >= 2) return launch_forward_v2(g, x, w, y, ep, s);   // conv_tc2.cu: tap groups + CTA pairs
+// w_mn == false: `w` is the K-major operand of this geometry, w[Cout][tap][cin_total].  w_mn == true: `g` is the adjoint of a
+// layer and `w` is THAT layer's KRSC weight [g.Cin = its Cout][tap][cin_total = its input channels]: this launch's output
+// channels are the weight's fastest index (ep.w_cin_offset / w_cin_total select the slice of them).
+int launch_forward(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, bool w_mn, cudaStream_t s) {
+    if (use_v2(g)) return launch_forward_v2(g, x, w, y, ep, w_mn, s);   // conv_tc2.cu: tap groups + CTA pairs
     ConvParams p;
     if (!forward_supported(g) || !build_taps(g, &p.taps, &p.in_stride, &p.out_stride, &p.GH, &p.GW)) return AGR_ERR_INVALID_ARGUMENT;
-    const int cin_total = ep.w_cin_total > 0 ? ep.w_cin_total : g.Cin;
-    if (ep.w_cin_offset < 0 || (ep.w_cin_offset % BK) || ep.w_cin_offset + g.Cin > cin_total) return AGR_ERR_INVALID_ARGUMENT;
+    const int wc = w_mn ? g.Cout : g.Cin;     // extent of this launch along the weight's fastest (channel) index
+    const int cin_total = ep.w_cin_total > 0 ? ep.w_cin_total : wc;
+    if (ep.w_cin_offset < 0 || (ep.w_cin_offset % BK) || ep.w_cin_offset + wc > cin_total) return AGR_ERR_INVALID_ARGUMENT;
     p.N = g.N; p.OH = g.OH; p.OW = g.OW; p.Cin = g.Cin; p.Cout = g.Cout;
     p.bias = ep.out_fp32 ? nullptr : ep.bias; p.noise = ep.out_fp32 ? nullptr : ep.noise; p.noise_w = ep.out_fp32 ? nullptr : ep.noise_w;
     p.residual = ep.residual; p.activate = ep.out_fp32 ? 0 : ep.activate; p.w_cin_offset = ep.w_cin_offset;
@@ -391,16 +408,23 @@ int launch_forward(const AgrConvGeom& g, const void* x, const void* w, void* y, 
     CUtensorMap mx, mw;
     if (!make_map_act(&mx, x, (uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N, TILE_W, TILE_H, (uint32_t)p.in_stride)) return AGR_ERR_CUDA;
     const int BN = (g.Cout % 128 == 0) ? 128 : 64;
-    if (!make_map_w(&mw, w, (uint64_t)cin_total, (uint64_t)(g.ksize * g.ksize), (uint64_t)g.Cout, BK, 1, (uint32_t)BN)) return AGR_ERR_CUDA;
+    if (w_mn) {   // KRSC weight of the adjoint layer: dims {its Cin = cin_total, taps, its Cout = g.Cin}; boxes {64 ci, 1, 64 co}
+        if (!make_map_w(&mw, w, (uint64_t)cin_total, (uint64_t)(g.ksize * g.ksize), (uint64_t)g.Cin, BK, 1, BK)) return AGR_ERR_CUDA;
+    } else if (!make_map_w(&mw, w, (uint64_t)cin_total, (uint64_t)(g.ksize * g.ksize), (uint64_t)g.Cout, BK, 1, (uint32_t)BN)) return AGR_ERR_CUDA;
     const long ctas = (long)p.N * ((p.GH + TILE_H - 1) / TILE_H) * ((p.GW + TILE_W - 1) / TILE_W) * (g.Cout / BN) * p.taps.n_phase;
     // 4 stages when the grid is a single wave (1 CTA/SM anyway), 3 stages (96 KB at BN=128) otherwise so that two CTAs
     // per SM overlap one's epilogue with the other's mainloop
-    if (BN == 64) return launch_s<64, 4>(mx, mw, p, s);
-    if (ctas <= 148) return launch_s<128, 4>(mx, mw, p, s);
-    return launch_s<128, 3>(mx, mw, p, s);
+    if (w_mn) {
+        if (BN == 64) return launch_s<64, 4, true>(mx, mw, p, s);
+        if (ctas <= 148) return launch_s<128, 4, true>(mx, mw, p, s);
+        return launch_s<128, 3, true>(mx, mw, p, s);
+    }
+    if (BN == 64) return launch_s<64, 4, false>(mx, mw, p, s);
+    if (ctas <= 148) return launch_s<128, 4, false>(mx, mw, p, s);
+    return launch_s<128, 3, false>(mx, mw, p, s);
 }
 
-static int g_wgrad_ctas = 2 * 148;
+static int g_wgrad_ctas = 2 * 148, g_wgrad_min_boxes = 16;   // measured best of {296,592,1184} x {8,16,32}: profiles/r02_conv_generations.txt
 
 bool wgrad_supported(const AgrConvGeom& g) {
     if (!geom_ok(g)) return false;
@@ -414,7 +438,7 @@ static int launch_w(const CUtensorMap& mx, const CUtensorMap& mdy, const WgradPa
         if (cudaFuncSetAttribute(conv_wgrad_tc_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
         attr = smem;
     }
-    dim3 grid((unsigned)p.slices, (unsigned)((p.Cin / MT) * (p.Cout / NT)), (unsigned)p.n_groups);
+    dim3 grid((unsigned)p.n_groups, (unsigned)((p.Cin / MT) * (p.Cout / NT)), (unsigned)p.slices);
     conv_wgrad_tc_kernel<MT, NT><<<grid, NUM_THREADS, smem, s>>>(mx, mdy, p);
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
@@ -456,8 +480,10 @@ int launch_wgrad(const AgrConvGeom& g, const void* x, const void* dy, float* dw,
     p.stages = stages;
     const long boxes = (long)g.N * ((p.GH + TILE_H - 1) / TILE_H) * ((p.GW + TILE_W - 1) / TILE_W);
     const long tiles = (long)(g.Cin / MT) * (g.Cout / NT) * ng;
-    long slices = (g_wgrad_ctas + tiles - 1) / tiles;       // ~2 waves of CTAs (1 CTA / SM), each with >= 2 pixel boxes when possible
-    if (slices > boxes / 2) slices = boxes / 2;
+    // split-K over pixel boxes: never more CTAs than the target (an extra partial wave costs a whole wave: 1 CTA / SM), and
+    // enough boxes per CTA that the fp32 reduction epilogue (3 taps x MT x NT REDs per CTA) stays a small part of its work
+    long slices = g_wgrad_ctas / tiles;
+    if (slices > boxes / g_wgrad_min_boxes) slices = boxes / g_wgrad_min_boxes;
     if (slices < 1) slices = 1;
     p.slices = (int)slices;
     CUtensorMap mx, mdy;
@@ -473,7 +499,8 @@ int launch_wgrad(const AgrConvGeom& g, const void* x, const void* dy, float* dw,
 }  // namespace tc
 }  // namespace agr
 
-extern "C" int agr_conv2d_set_wgrad_ctas(int32_t ctas) {
-    if (ctas > 0) agr::tc::g_wgrad_ctas = ctas;
+extern "C" int agr_conv2d_set_wgrad_split(int32_t max_ctas, int32_t min_boxes) {
+    if (max_ctas > 0) agr::tc::g_wgrad_ctas = max_ctas;
+    if (min_boxes > 0) agr::tc::g_wgrad_min_boxes = min_boxes;
     return agr::tc::g_wgrad_ctas;
 }

@@ -100,7 +100,8 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t base) {
 }
 
 // BN: output channels of the tile (of the pair's tile in pair mode).  PAIR: two CTAs per tcgen05.mma (cluster 2x1x1).
-template <int BN, bool PAIR>
+// B_MN: weight operand read MN-major from the adjoint layer's KRSC tensor (see conv_tc_kernel in conv_tc.cu).
+template <int BN, bool PAIR, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ Params p) {
     constexpr int BNL = PAIR ? BN / 2 : BN;                  // weight rows this CTA stages
@@ -160,13 +161,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)(a_bytes + grp.ntaps * B_BYTES));
                     const uint32_t bar = mapa_rank0(smem_u32(&full_bar[s]));
                     tma_load_4d_pair(a_dst, &map_x, bar, ck * BK, x0, y0, img);
-                    for (int t = 0; t < grp.ntaps; ++t)
-                        tma_load_3d_pair(b_dst + t * B_BYTES, &map_w, bar, p.w_cin_offset + ck * BK, grp.wt[t], n0 + (int)rank * BNL);
+                    for (int t = 0; t < grp.ntaps; ++t) {
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BNL / 64; ++j)
+                                tma_load_3d_pair(b_dst + t * B_BYTES + j * (64 * BK * 2), &map_w, bar, p.w_cin_offset + n0 + (int)rank * BNL + 64 * j, grp.wt[t], ck * BK);
+                        } else {
+                            tma_load_3d_pair(b_dst + t * B_BYTES, &map_w, bar, p.w_cin_offset + ck * BK, grp.wt[t], n0 + (int)rank * BNL);
+                        }
+                    }
                 } else {
                     mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + grp.ntaps * B_BYTES));
                     tma_load_4d(a_dst, &map_x, &full_bar[s], ck * BK, x0, y0, img);
-                    for (int t = 0; t < grp.ntaps; ++t)
-                        tma_load_3d(b_dst + t * B_BYTES, &map_w, &full_bar[s], p.w_cin_offset + ck * BK, grp.wt[t], n0);
+                    for (int t = 0; t < grp.ntaps; ++t) {
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BNL / 64; ++j)
+                                tma_load_3d(b_dst + t * B_BYTES + j * (64 * BK * 2), &map_w, &full_bar[s], p.w_cin_offset + n0 + 64 * j, grp.wt[t], ck * BK);
+                        } else {
+                            tma_load_3d(b_dst + t * B_BYTES, &map_w, &full_bar[s], p.w_cin_offset + ck * BK, grp.wt[t], n0);
+                        }
+                    }
                 }
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
@@ -174,7 +189,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     } else if (warp == 1) {
         // ================= MMA issuer (one elected lane; in pair mode of the leader CTA only) =================
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = umma_idesc(PAIR ? 2 * BM : BM, BN, 0);
+            const uint32_t idesc = umma_idesc2(PAIR ? 2 * BM : BM, BN, 0, B_MN ? 1 : 0);
             int s = 0; uint32_t ph = 0;
             uint32_t acc = 0;
             for (int it = 0; it < num_it; ++it) {
@@ -184,11 +199,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t b_addr = a_addr + A_SLOT;
                 for (int t = 0; t < ntaps; ++t) {
-                    const uint64_t adesc = umma_desc(a_addr + t * ROW_BYTES, 16), bdesc = umma_desc(b_addr + t * B_BYTES, 16);
+                    const uint64_t adesc = umma_desc(a_addr + t * ROW_BYTES, 16), bdesc = umma_desc(b_addr + t * B_BYTES, B_MN ? 64 * BK * 2 : 16);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {  // UMMA_K = 16 bf16 = 32 B -> +2 in the (>>4) start-address field
-                        if (PAIR) umma_f16_pair(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
-                        else umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                    for (int k = 0; k < BK / 16; ++k) {  // UMMA_K = 16: +32 B along a K-major row, +16 rows (2048 B) of an MN-major tile
+                        if (PAIR) umma_f16_pair(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc, acc);
+                        else umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc, acc);
                         acc = 1;
                     }
                 }
@@ -341,7 +356,7 @@ static bool make_map_w(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool B_MN>
 static int launch_k(const CUtensorMap& mx, const CUtensorMap& mw, Params& p, long tiles, cudaStream_t s) {
     constexpr int BNL = PAIR ? BN / 2 : BN;
     constexpr int stage_bytes = A_SLOT + 3 * BNL * BK * 2;
@@ -356,7 +371,7 @@ static int launch_k(const CUtensorMap& mx, const CUtensorMap& mw, Params& p, lon
     const int smem = stages * stage_bytes + 1024;
     static int attr = 0;
     if (attr < smem) {
-        if (cudaFuncSetAttribute(conv_tc2_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
+        if (cudaFuncSetAttribute(conv_tc2_kernel<BN, PAIR, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
         attr = smem;
     }
     cudaLaunchConfig_t cfg = {};
@@ -368,58 +383,314 @@ static int launch_k(const CUtensorMap& mx, const CUtensorMap& mw, Params& p, lon
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = PAIR ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BN, PAIR>, mx, mw, p) != cudaSuccess) return AGR_ERR_CUDA;
+    if (cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BN, PAIR, B_MN>, mx, mw, p) != cudaSuccess) return AGR_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
 }
 
 }  // namespace v2
 
-// AGR_CONV_TC: 1 = conv_tc_kernel (first generation), 2 = tap groups without pairs, 3 (default) = tap groups + CTA pairs
+// ---- persistent variant for the 64-output-channel layers -------------------------------------------------------------------
+// The layers with Cout = 64 at 512^2 x 16 views have 32 768 pixel tiles with a SHORT contraction each (9 taps x 64 or 128
+// channels): one tile per CTA is bound by the per-CTA latency chain (launch, barrier init, TMEM allocation, the first TMA
+// round trip, the epilogue) and not by any throughput.  Here one CTA per SM walks a strided list of tiles with
+//   * the whole weight (taps x Cin x 64, 72 or 144 KB) resident in shared memory, loaded once;
+//   * the producer warp running ahead across tile boundaries through a ring of haloed pixel boxes (tap groups, see above);
+//   * TWO accumulators in TMEM (2 x 64 columns): the epilogue of tile i overlaps the MMAs of tile i + 1.
+// Steady state per tile: 3 boxes x 20 KB from L2, 36 tcgen05.mma (128 x 64 x 16), one 128 x 64 epilogue.
+namespace v3 {
+using namespace v2;
+
+constexpr int W_TILE = 64 * BK * 2;      // 8 KB: 64 output channels x 64 input channels of one tap
+constexpr int MAX_STAGES3 = 8;
+
+struct Params3 {
+    Params c;               // geometry, tap groups, epilogue (c.stages = A ring depth)
+    int kk;                 // taps of the weight (ksize^2)
+    int n_wtiles;           // kk * Cin / 64
+    int total_tiles;        // N * tiles per image * phases
+};
+
+template <bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ Params3 q) {
+    constexpr int BN = 64;
+    const Params& p = q.c;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* w_smem = smem;                                  // [wt][ck] tiles of 8 KB
+    unsigned char* a_ring = smem + (size_t)q.n_wtiles * W_TILE;    // stages x A_SLOT
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES3], empty_bar[MAX_STAGES3], w_bar, tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_w = (p.GW + TILE_W - 1) / TILE_W;
+    const int tiles_img = tiles_w * ((p.GH + TILE_H - 1) / TILE_H);
+    const int kchunks = p.Cin / BK;
+    const int STAGES = p.stages;
+    const int a_bytes = p.rows * ROW_BYTES;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&w_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+    }
+    if (warp == 1) tmem_alloc<2 * BN>(&tmem_base_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ================= producer: the weight once, then pixel boxes across all of this CTA's tiles =================
+        if (lane == 0) {
+            mbar_expect_tx(&w_bar, (uint32_t)(q.n_wtiles * W_TILE));
+            for (int wt = 0; wt < q.kk; ++wt)
+                for (int ck = 0; ck < kchunks; ++ck) {
+                    unsigned char* dst = w_smem + (size_t)(wt * kchunks + ck) * W_TILE;
+                    if (B_MN) tma_load_3d(dst, &map_w, &w_bar, p.w_cin_offset, wt, ck * BK);
+                    else tma_load_3d(dst, &map_w, &w_bar, p.w_cin_offset + ck * BK, wt, 0);
+                }
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
+                const int phase = tile % p.n_phase, rest = tile / p.n_phase;
+                const int img = rest / tiles_img, tile_m = rest - img * tiles_img;
+                const int h0 = (tile_m / tiles_w) * TILE_H, w0 = (tile_m % tiles_w) * TILE_W;
+                for (int g = p.gbegin[phase]; g < p.gbegin[phase + 1]; ++g) {
+                    const int x0 = p.in_stride * w0 + p.groups[g].dx, y0 = p.in_stride * h0 + p.groups[g].dy;
+                    for (int ck = 0; ck < kchunks; ++ck) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_expect_tx(&full_bar[s], (uint32_t)a_bytes);
+                        tma_load_4d(a_ring + (size_t)s * A_SLOT, &map_x, &full_bar[s], ck * BK, x0, y0, img);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc2(BM, BN, 0, B_MN ? 1 : 0);
+            mbar_wait(&w_bar, 0);
+            tc_fence_after();
+            const uint32_t w_addr = smem_u32(w_smem);
+            int s = 0; uint32_t ph = 0;
+            int tl = 0;
+            for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tl) {
+                const int phase = tile % p.n_phase;
+                const int buf = tl & 1;
+                mbar_wait(&tempty_bar[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));     // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                uint32_t acc = 0;
+                for (int g = p.gbegin[phase]; g < p.gbegin[phase + 1]; ++g) {
+                    const TapGroup grp = p.groups[g];
+                    for (int ck = 0; ck < kchunks; ++ck) {
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(a_ring + (size_t)s * A_SLOT);
+                        for (int t = 0; t < grp.ntaps; ++t) {
+                            const uint64_t adesc = umma_desc(a_addr + t * ROW_BYTES, 16);
+                            const uint64_t bdesc = umma_desc(w_addr + (uint32_t)((grp.wt[t] * kchunks + ck) * W_TILE), B_MN ? W_TILE : 16);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc, acc);
+                                acc = 1;
+                            }
+                        }
+                        umma_commit(&empty_bar[s]);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+                umma_commit(&tfull_bar[buf]);
+            }
+        }
+    } else {
+        // ================= epilogue warps: drain accumulator (tl & 1) while the next tile's MMAs fill the other =================
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const float slope_gain = p.activate == 1 ? 1.4142135623730951f : 1.f;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tl) {
+            const int phase = tile % p.n_phase, rest = tile / p.n_phase;
+            const int img = rest / tiles_img, tile_m = rest - img * tiles_img;
+            const int h0 = (tile_m / tiles_w) * TILE_H, w0 = (tile_m % tiles_w) * TILE_W;
+            const int buf = tl & 1;
+            mbar_wait(&tfull_bar[buf], (uint32_t)((tl >> 1) & 1));
+            tc_fence_after();
+            const int oy = (h0 + row / TILE_W) * p.out_stride + p.py[phase];
+            const int ox = (w0 + row % TILE_W) * p.out_stride + p.px[phase];
+            const bool valid = oy < p.OH && ox < p.OW;
+            const size_t pix = (size_t)oy * p.OW + ox;
+            const float add = (valid && p.noise && p.noise_w) ? p.noise_w[0] * p.noise[pix] : 0.f;
+            const size_t opix = (size_t)img * p.OH * p.OW + pix;
+            __nv_bfloat16* out = p.y + opix * p.Cout;
+            const float* res = p.residual ? p.residual + pix * p.Cout : nullptr;
+            float* out32 = p.y_f32 ? p.y_f32 + opix * p.Cout : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+                tmem_wait_ld();
+                if (!valid) continue;
+                if (res) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 rr = reinterpret_cast<const float4*>(res + c0)[i];
+                        r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + rr.x);
+                        r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + rr.y);
+                        r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + rr.z);
+                        r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + rr.w);
+                    }
+                }
+                if (out32) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        reinterpret_cast<float4*>(out32 + c0)[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                    continue;
+                }
+                uint4 packed[4];
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(packed);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float v0 = __uint_as_float(r[2 * i]) + add, v1 = __uint_as_float(r[2 * i + 1]) + add;
+                    if (p.bias) { v0 += p.bias[c0 + 2 * i]; v1 += p.bias[c0 + 2 * i + 1]; }
+                    if (p.activate) {
+                        v0 = (v0 > 0.f ? v0 : 0.2f * v0) * slope_gain;
+                        v1 = (v1 > 0.f ? v1 : 0.2f * v1) * slope_gain;
+                    }
+                    h2[i] = __floats2bfloat162_rn(v0, v1);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(out + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = packed[i];
+            }
+            tc_fence_before();                 // this warp's tcgen05.ld of the accumulator are complete (wait::ld above)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * BN>(tmem_base);
+    }
+}
+
+template <bool B_MN>
+static int launch_p(const CUtensorMap& mx, const CUtensorMap& mw, Params3& q, cudaStream_t s) {
+    const int w_bytes = q.n_wtiles * W_TILE;
+    int stages = (MAX_SMEM - 1024 - w_bytes) / A_SLOT;
+    if (stages > MAX_STAGES3) stages = MAX_STAGES3;
+    if (stages < 3) return AGR_ERR_INVALID_ARGUMENT;
+    q.c.stages = stages;
+    const int smem = w_bytes + stages * A_SLOT + 1024;
+    static int attr = 0;
+    if (attr < smem) {
+        if (cudaFuncSetAttribute(conv_tc3_kernel<B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return AGR_ERR_CUDA;
+        attr = smem;
+    }
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); static int cached = 0; if (!cached) cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev); if (cached > 0) sms = cached; }
+    const int grid = q.total_tiles < sms ? q.total_tiles : sms;
+    conv_tc3_kernel<B_MN><<<grid, NUM_THREADS, smem, s>>>(mx, mw, q);
+    return cudaGetLastError() == cudaSuccess ? AGR_OK : AGR_ERR_CUDA;
+}
+
+}  // namespace v3
+
+// AGR_CONV_TC / agr_conv2d_set_generation: 1 = conv_tc_kernel always, 2 = tap groups always, 3 = tap groups + CTA pairs always,
+// 0 (default) = by shape: measured on B200 (tools/bench_conv.py, profiles/r02_conv_generations.txt) the pair kernel wins where
+// the contraction is long and there are enough pixel tiles to fill the SMs with pairs; elsewhere one box per tap with two
+// CTAs per SM is as fast or faster (short contractions are bound by per-CTA latency, not by L2 -> shared-memory bytes).
 static int g_generation = -1;
 
 int conv_tc_generation() {
     if (g_generation < 0) {
         const char* e = getenv("AGR_CONV_TC");
-        g_generation = e ? atoi(e) : 3;
-        if (g_generation < 1 || g_generation > 3) g_generation = 3;
+        g_generation = e ? atoi(e) : 0;
+        if (g_generation < 0 || g_generation > 3) g_generation = 0;
     }
     return g_generation;
 }
 
-int launch_forward_v2(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, cudaStream_t s) {
+// The persistent 64-channel kernel is OFF unless AGR_CONV_PERSISTENT=1: on B200 it measured the same as one tile per CTA on
+// the 16 x 512^2 64 -> 64 layer (0.81 vs 0.81 ms) and slower on the transposed 128 -> 64 layer (0.86 vs 0.73 ms) —
+// profiles/r02_conv_generations.txt; the layer is not bound by what this kernel removes.
+static int g_persistent = -1;
+
+// Persistent kernel: Cout = 64, the whole weight fits next to a >= 3-deep box ring, and there are several waves of tiles.
+static bool use_v3(const AgrConvGeom& g) {
+    if (g_persistent < 0) { const char* e = getenv("AGR_CONV_PERSISTENT"); g_persistent = e ? atoi(e) : 0; }
+    if (!g_persistent || conv_tc_generation() != 0) return false;
+    if (g.Cout != 64 || g.Cin % 64 || g.Cin > 128) return false;
+    const int s = g.transposed ? g.stride : 1;
+    const long tiles = (long)g.N * (((g.OH + s - 1) / s + v2::TILE_H - 1) / v2::TILE_H) * (((g.OW + s - 1) / s + v2::TILE_W - 1) / v2::TILE_W) * s * s;
+    return tiles >= 4 * 148 && g.ksize * g.ksize * (g.Cin / 64) * v3::W_TILE + 3 * v2::A_SLOT + 1024 <= v2::MAX_SMEM;
+}
+
+bool use_v2(const AgrConvGeom& g) {
+    if (use_v3(g)) return true;
+    const int gen = conv_tc_generation();
+    if (gen) return gen >= 2;
+    if (g.stride != 1 || g.ksize != 3) return false;   // (the data gradient of a stride-1 layer arrives as transposed, stride 1)
+    const long tiles = (long)g.N * ((g.OH + v2::TILE_H - 1) / v2::TILE_H) * ((g.OW + v2::TILE_W - 1) / v2::TILE_W);
+    return g.Cin >= 256 && g.Cout % 128 == 0 && tiles >= 128 && tiles % 2 == 0;
+}
+
+int launch_forward_v2(const AgrConvGeom& g, const void* x, const void* w, void* y, const AgrConvEpilogue& ep, bool w_mn, cudaStream_t s) {
     using namespace v2;
     Params p;
     if (!geom_ok(g) || g.Cin % BK || g.Cout % 64 || !build_groups(g, &p)) return AGR_ERR_INVALID_ARGUMENT;
-    const int cin_total = ep.w_cin_total > 0 ? ep.w_cin_total : g.Cin;
-    if (ep.w_cin_offset < 0 || (ep.w_cin_offset % BK) || ep.w_cin_offset + g.Cin > cin_total) return AGR_ERR_INVALID_ARGUMENT;
+    const int wc = w_mn ? g.Cout : g.Cin;
+    const int cin_total = ep.w_cin_total > 0 ? ep.w_cin_total : wc;
+    if (ep.w_cin_offset < 0 || (ep.w_cin_offset % BK) || ep.w_cin_offset + wc > cin_total) return AGR_ERR_INVALID_ARGUMENT;
     p.N = g.N; p.OH = g.OH; p.OW = g.OW; p.Cin = g.Cin; p.Cout = g.Cout;
     p.bias = ep.out_fp32 ? nullptr : ep.bias; p.noise = ep.out_fp32 ? nullptr : ep.noise; p.noise_w = ep.out_fp32 ? nullptr : ep.noise_w;
     p.residual = ep.residual; p.activate = ep.out_fp32 ? 0 : ep.activate; p.w_cin_offset = ep.w_cin_offset;
     p.y = ep.out_fp32 ? nullptr : static_cast<__nv_bfloat16*>(y);
     p.y_f32 = ep.out_fp32 ? static_cast<float*>(y) : nullptr;
     const long tiles = (long)p.N * ((p.GH + TILE_H - 1) / TILE_H) * ((p.GW + TILE_W - 1) / TILE_W);
-    const bool pair = conv_tc_generation() >= 3 && (tiles % 2 == 0);
+    if (use_v3(g)) {
+        v3::Params3 q;
+        q.c = p; q.kk = g.ksize * g.ksize; q.n_wtiles = q.kk * (g.Cin / BK); q.total_tiles = (int)(tiles * p.n_phase);
+        CUtensorMap mx3, mw3;
+        if (!make_map_act(&mx3, x, (uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N, TILE_W, (uint32_t)p.rows, (uint32_t)p.in_stride)) return AGR_ERR_CUDA;
+        if (!make_map_w(&mw3, w, (uint64_t)cin_total, (uint64_t)q.kk, (uint64_t)(w_mn ? g.Cin : g.Cout), BK, 1, BK)) return AGR_ERR_CUDA;
+        return w_mn ? v3::launch_p<true>(mx3, mw3, q, s) : v3::launch_p<false>(mx3, mw3, q, s);
+    }
     // channel tile: as wide as the layer allows while the grid still covers the SMs (a pair mode CTA stages BN/2 weight rows)
     int BN = 64;
     if (g.Cout % 128 == 0) BN = 128;
+    // an MN-major weight tile is made of whole 64-channel atoms: a pair needs BN >= 128
+    const bool pair = conv_tc_generation() != 2 && (tiles % 2 == 0) && !(w_mn && BN < 128);
     if (pair && g.Cout % 256 == 0 && tiles * (g.Cout / 256) * p.n_phase >= 120) BN = 256;
     CUtensorMap mx, mw;
     if (!make_map_act(&mx, x, (uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N, TILE_W, (uint32_t)p.rows, (uint32_t)p.in_stride)) return AGR_ERR_CUDA;
     const int bnl = pair ? BN / 2 : BN;
-    if (!make_map_w(&mw, w, (uint64_t)cin_total, (uint64_t)(g.ksize * g.ksize), (uint64_t)g.Cout, BK, 1, (uint32_t)bnl)) return AGR_ERR_CUDA;
-    if (pair) {
-        if (BN == 256) return launch_k<256, true>(mx, mw, p, tiles, s);
-        if (BN == 128) return launch_k<128, true>(mx, mw, p, tiles, s);
-        return launch_k<64, true>(mx, mw, p, tiles, s);
+    if (w_mn) {
+        if (!make_map_w(&mw, w, (uint64_t)cin_total, (uint64_t)(g.ksize * g.ksize), (uint64_t)g.Cin, BK, 1, BK)) return AGR_ERR_CUDA;
+    } else if (!make_map_w(&mw, w, (uint64_t)cin_total, (uint64_t)(g.ksize * g.ksize), (uint64_t)g.Cout, BK, 1, (uint32_t)bnl)) return AGR_ERR_CUDA;
+    if (w_mn) {
+        if (pair) return BN == 256 ? launch_k<256, true, true>(mx, mw, p, tiles, s) : launch_k<128, true, true>(mx, mw, p, tiles, s);
+        return BN == 128 ? launch_k<128, false, true>(mx, mw, p, tiles, s) : launch_k<64, false, true>(mx, mw, p, tiles, s);
     }
-    if (BN == 128) return launch_k<128, false>(mx, mw, p, tiles, s);
-    return launch_k<64, false>(mx, mw, p, tiles, s);
+    if (pair) {
+        if (BN == 256) return launch_k<256, true, false>(mx, mw, p, tiles, s);
+        if (BN == 128) return launch_k<128, true, false>(mx, mw, p, tiles, s);
+        return launch_k<64, true, false>(mx, mw, p, tiles, s);
+    }
+    if (BN == 128) return launch_k<128, false, false>(mx, mw, p, tiles, s);
+    return launch_k<64, false, false>(mx, mw, p, tiles, s);
 }
 
 }  // namespace tc
 }  // namespace agr
 
 extern "C" int agr_conv2d_set_generation(int32_t generation) {
-    if (generation >= 1 && generation <= 3) agr::tc::g_generation = generation;
+    if (generation >= 0 && generation <= 3) agr::tc::g_generation = generation;
     return agr::tc::conv_tc_generation();
 }

@@ -126,3 +126,124 @@ def load_ckpt(path, avatar_net, optimizer=None, map_location="cpu"):
         if "avatar_net" in sd:
             optimizer.load_state_dict(sd["avatar_net"])
     return net.get("epoch_idx", 0), net.get("iter_idx", 0)
+
+
+# ------------------------------------------------------------------------------------------ OpenEXR position maps
+# The SMPL position maps the datasets store (dataset/dataset_mv_rgb.py:146-151: cv.imread(.../smpl_pos_map/%08d.exr,
+# cv.IMREAD_UNCHANGED), written by gen_data/gen_pos_maps.py with cv.imwrite) are single-part scan-line OpenEXR files with
+# FLOAT channels and ZIP compression (what OpenCV writes).  The reader below decodes that container directly — no OpenEXR
+# library, no OpenCV — and returns what cv.imread(..., IMREAD_UNCHANGED) returns: (H, W, C) float32 with the channels in
+# B, G, R[, A] order.  Pinned against OpenCV's own decoder (tests/test_formats.py: a committed cv2-written fixture, and a
+# live comparison when cv2 is importable).
+_EXR_MAGIC = 20000630
+_EXR_LINES_PER_BLOCK = {0: 1, 1: 1, 2: 1, 3: 16}      # NONE, RLE, ZIPS, ZIP
+
+
+def _exr_header(buf):
+    import struct
+    magic, version = struct.unpack_from("<II", buf, 0)
+    if magic != _EXR_MAGIC:
+        raise ValueError("not an OpenEXR file")
+    if version & 0x200 or version & 0x800 or version & 0x1000:
+        raise ValueError("tiled / deep / multi-part OpenEXR files are not position maps; only scan-line images are read")
+    attrs, i = {}, 8
+    while True:
+        j = buf.index(b"\0", i)
+        name = buf[i:j].decode()
+        if not name:
+            return attrs, j + 1
+        k = buf.index(b"\0", j + 1)
+        typ = buf[j + 1:k].decode()
+        size = struct.unpack_from("<i", buf, k + 1)[0]
+        attrs[name] = (typ, buf[k + 5:k + 5 + size])
+        i = k + 5 + size
+
+
+def _exr_unzip(raw, expect):
+    import zlib
+    if len(raw) == expect:                 # the writer stores a block raw when compression does not shrink it
+        return np.frombuffer(raw, np.uint8)
+    t = np.frombuffer(zlib.decompress(raw), np.uint8)
+    if t.size != expect:
+        raise ValueError("OpenEXR block decompressed to %d bytes, expected %d" % (t.size, expect))
+    t = (np.cumsum(t.astype(np.int64) - 128) + 128).astype(np.uint8)       # undo the byte-delta predictor: t[i] += t[i-1] - 128
+    half = (expect + 1) // 2
+    out = np.empty(expect, np.uint8)                                       # undo the even/odd byte split
+    out[0::2] = t[:half]
+    out[1::2] = t[half:]
+    return out
+
+
+def _exr_unrle(raw, expect):
+    if len(raw) == expect:
+        return np.frombuffer(raw, np.uint8)
+    out, i = bytearray(), 0
+    while i < len(raw):
+        n = raw[i] - 256 if raw[i] > 127 else raw[i]
+        i += 1
+        if n < 0:
+            out += raw[i:i - n]
+            i -= n
+        else:
+            out += bytes([raw[i]]) * (n + 1)
+            i += 1
+    t = np.frombuffer(bytes(out), np.uint8)
+    t = (np.cumsum(t.astype(np.int64) - 128) + 128).astype(np.uint8)
+    half = (expect + 1) // 2
+    res = np.empty(expect, np.uint8)
+    res[0::2] = t[:half]
+    res[1::2] = t[half:]
+    return res
+
+
+def read_exr(path):
+    """-> (H, W, C) float32 like cv.imread(path, cv.IMREAD_UNCHANGED): channels B, G, R[, A] for colour images, the file's
+    (alphabetical) channel order otherwise; (H, W) for a single channel.  HALF channels are widened to float32."""
+    import struct
+    buf = open(path, "rb").read()
+    attrs, pos = _exr_header(buf)
+    comp = attrs["compression"][1][0]
+    if comp not in _EXR_LINES_PER_BLOCK:
+        raise ValueError("OpenEXR compression %d is not supported (NONE, RLE, ZIPS, ZIP are)" % comp)
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    W, H = x1 - x0 + 1, y1 - y0 + 1
+    chans, c = [], attrs["channels"][1]
+    i = 0
+    while c[i] != 0:
+        j = c.index(b"\0", i)
+        ptype, _plinear, xs, ys = struct.unpack_from("<iB3xii", c, j + 1)
+        if xs != 1 or ys != 1 or ptype not in (1, 2):
+            raise ValueError("OpenEXR channel %r: only unsampled HALF / FLOAT channels are read" % c[i:j])
+        chans.append((c[i:j].decode(), ptype))
+        i = j + 17
+    bpp = [2 if t == 1 else 4 for _, t in chans]
+    line_bytes = W * sum(bpp)
+    lines = _EXR_LINES_PER_BLOCK[comp]
+    n_blocks = (H + lines - 1) // lines
+    offsets = struct.unpack_from("<%dQ" % n_blocks, buf, pos)
+    planes = [np.empty((H, W), np.float32) for _ in chans]
+    for off in offsets:
+        y, size = struct.unpack_from("<ii", buf, off)
+        rows = min(lines, y1 + 1 - y)
+        raw = buf[off + 8:off + 8 + size]
+        data = raw if comp == 0 else (_exr_unrle(raw, rows * line_bytes) if comp == 1 else _exr_unzip(raw, rows * line_bytes))
+        data = np.frombuffer(bytes(data), np.uint8).reshape(rows, line_bytes)
+        o = 0
+        for ci, ((_, ptype), b) in enumerate(zip(chans, bpp)):
+            seg = np.ascontiguousarray(data[:, o:o + W * b])
+            planes[ci][y - y0:y - y0 + rows] = seg.view("<f2" if ptype == 1 else "<f4").astype(np.float32).reshape(rows, W)
+            o += W * b
+    names = [n for n, _ in chans]
+    order = [names.index(n) for n in ("B", "G", "R", "A") if n in names] if {"B", "G", "R"} <= set(names) else list(range(len(names)))
+    if len(order) == 1:
+        return planes[order[0]]
+    return np.stack([planes[k] for k in order], axis=-1)
+
+
+def load_smpl_pos_map(path, device="cpu"):
+    """The per-pose input of the three U-Nets as the dataset builds it (dataset_mv_rgb.py:146-151): the (H, 2H, 3) position
+    map split into its front | back halves and stacked on the channel axis -> (6, H, H) float32."""
+    m = read_exr(path)
+    h = m.shape[1] // 2
+    pos_map = np.concatenate([m[:, :h], m[:, h:]], axis=2).transpose(2, 0, 1)
+    return torch.from_numpy(np.ascontiguousarray(pos_map, dtype=np.float32)).to(device)

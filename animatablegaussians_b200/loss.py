@@ -61,3 +61,44 @@ def photometric_loss(rgb_maps, mask_maps, color_imgs, mask_imgs, boundary_mask_i
     if not rgb_maps.is_cuda:
         raise RuntimeError("photometric_loss runs on the GPU only (no CPU fallback)")
     return _PhotometricLoss.apply(rgb_maps, mask_maps, color_imgs, mask_imgs, boundary_mask_imgs, bg_color, w_l1, w_mask)
+
+
+def crop_image(gt_mask, patch_size, randomly, *images, bg_color=None, generator=None):
+    """Patch crop in front of the perceptual loss, as the trainer does it (main_avatar.py:75-115): the bounding box of
+    `gt_mask > 0` ((H, W)) is cut from every (3, H, W) image, centred on a square `bg_color` canvas of the box's longer
+    side, and either resized to `patch_size` (bilinear) or — `randomly` and the square larger than the patch — a random
+    patch_size window of it is taken (the same window for every image).  Returns a list (one tensor if one image).
+
+    Like the reference, the box comes back to the host once per call (its corner indices size the canvas).  The box is read
+    from row / column occupancy instead of `argwhere` (same four numbers, no (n, 2) index list)."""
+    import torch.nn.functional as F
+    if not images:
+        raise ValueError("crop_image: no images")
+    occ = gt_mask > 0.
+    rows, cols = occ.any(1), occ.any(0)
+    if not bool(rows.any()):
+        raise ValueError("crop_image: empty mask")     # the reference fails here too (min of an empty tensor)
+    r, c = torch.nonzero(rows).flatten(), torch.nonzero(cols).flatten()
+    min_v, max_v, min_u, max_u = int(r[0]), int(r[-1]), int(c[0]), int(c[-1])
+    len_v, len_u = max_v - min_v, max_u - min_u       # exclusive of the last row / column, as the reference slices
+    max_size = max(len_v, len_u)
+    window = randomly and max_size > patch_size
+    if window:
+        rv = int(torch.randint(0, max_size - patch_size + 1, (1,), generator=generator))
+        ru = int(torch.randint(0, max_size - patch_size + 1, (1,), generator=generator))
+    out = []
+    for image in images:
+        bg = torch.zeros(3, dtype=image.dtype, device=image.device) if bg_color is None else bg_color.to(image)
+        canvas = bg[:, None, None] * torch.ones((3, max_size, max_size), dtype=image.dtype, device=image.device)
+        if len_v > len_u:
+            s = (max_size - len_u) // 2
+            canvas[:, :, s:s + len_u] = image[:, min_v:max_v, min_u:max_u]
+        else:
+            s = (max_size - len_v) // 2
+            canvas[:, s:s + len_v, :] = image[:, min_v:max_v, min_u:max_u]
+        if window:
+            canvas = canvas[:, rv:rv + patch_size, ru:ru + patch_size]
+        else:
+            canvas = F.interpolate(canvas[None], size=(patch_size, patch_size), mode="bilinear")[0]
+        out.append(canvas)
+    return out if len(out) > 1 else out[0]

@@ -782,10 +782,11 @@ _lib.register_symbols({
     "agr_conv2d_path": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), C.c_int32]),
     "agr_conv2d_forward": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), _p, _p, _p, C.POINTER(AgrConvEpilogue), _p]),
     "agr_conv2d_dgrad": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), _p, _p, _p, _p]),
+    "agr_conv2d_dgrad_krsc": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), _p, _p, C.c_int32, C.c_int32, _p, _p]),
     "agr_conv2d_wgrad": (C.c_int, [C.c_int32, C.POINTER(AgrConvGeom), _p, _p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
     "agr_weight_transpose": (C.c_int, [C.c_int32, _p, _p, C.c_int32, C.c_int32, C.c_int32, _p]),
     "agr_conv2d_set_generation": (C.c_int, [C.c_int32]),
-    "agr_conv2d_set_wgrad_ctas": (C.c_int, [C.c_int32]),
+    "agr_conv2d_set_wgrad_split": (C.c_int, [C.c_int32, C.c_int32]),
 })
 
 _STAGE = {1: "styleunet_conv_tc", 2: "styleunet_conv_direct"}
@@ -847,6 +848,22 @@ def conv_dgrad(dy, wt, g):
     stats.add_work(stage, _flops(g))
     with torch.cuda.device(dy.device), stats.stage(stage, launches=1, label=_label("dgrad", g)):
         _check(lib.agr_conv2d_dgrad(_code(dy), C.byref(g), _ptr(dy), _ptr(wt), _ptr(dx), _stream(dy)), "agr_conv2d_dgrad")
+    return dx
+
+
+def conv_dgrad_w(dy, w, g, cin_total=0, cin_offset=0):
+    """dx of the layer `g` from dy and the layer's KRSC operand `w` itself.  Tensor-core path: the weight is read in place
+    (agr_conv2d_dgrad_krsc); CUDA-core path: through a transposed copy, as before.  `cin_total/cin_offset`: `g.Cin` is a
+    slice of the weight's input channels (split contraction)."""
+    if conv_path(dy, g, 1) != 1:
+        wt = weight_transpose(w)
+        return conv_dgrad(dy, wt if not cin_total else wt[cin_offset:cin_offset + g.Cin], g)
+    lib = _lib.load()
+    dx = torch.empty((g.N, g.Cin, g.H, g.W), dtype=dy.dtype, device=dy.device, memory_format=_CL)
+    stats.add_work("styleunet_conv_tc", _flops(g))
+    with torch.cuda.device(dy.device), stats.stage("styleunet_conv_tc", launches=1, label=_label("dgrad", g)):
+        _check(lib.agr_conv2d_dgrad_krsc(_code(dy), C.byref(g), _ptr(dy), _ptr(w), int(cin_total), int(cin_offset), _ptr(dx), _stream(dy)),
+               "agr_conv2d_dgrad_krsc")
     return dx
 
 
@@ -918,7 +935,7 @@ class _Conv(torch.autograd.Function):
         dz, db, dn = _act_backward(gy, y, nz, activate, has_b, has_n, g.Cout)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = conv_dgrad(dz, weight_transpose(w), g)
+            dx = conv_dgrad_w(dz, w, g)
         if ctx.needs_input_grad[2 if has_handle else 1]:
             dw = _as_kcrs(conv_wgrad(x, dz, g))
         return (dx, None if has_handle else dw, dw if has_handle else None, (db.view(bshape) if has_b else None), None,
@@ -961,9 +978,8 @@ class _SplitConvAct(torch.autograd.Function):
         dzs = _new_like(dz[:1], Cout, dz.shape[2], dz.shape[3])
         with torch.cuda.device(g.device), stats.stage("styleunet_act", launches=1):
             _check(lib.agr_sum_batch(_code(dz), _ptr(dz), _ptr(dzs), V, dzs.numel(), _stream(g)), "agr_sum_batch")
-        wt = weight_transpose(w)                       # (Ca+Cb, Cout, k, k): rows = input channels
-        da = conv_dgrad(dz, wt[:Ca], ga) if ctx.needs_input_grad[0] else None
-        dbb = conv_dgrad(dzs, wt[Ca:], gb) if ctx.needs_input_grad[1] else None
+        da = conv_dgrad_w(dz, w, ga, Ca + Cb, 0) if ctx.needs_input_grad[0] else None     # w (Cout, Ca+Cb, k, k): slices of its input channels
+        dbb = conv_dgrad_w(dzs, w, gb, Ca + Cb, Ca) if ctx.needs_input_grad[1] else None
         dw = None
         if ctx.needs_input_grad[3 if has_handle else 2]:
             dwf = conv_wgrad(a, dz, ga, ci_total=Ca + Cb, ci_offset=0)

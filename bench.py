@@ -461,6 +461,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json configs, 1-based: 4 = the headline train step (default), 5 = 500k Gaussians x 24 views; 1-3: auxiliary lines")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="StyleUNet compute dtype of the product arm: bf16 (tcgen05, the headline) or fp32 (CUDA-core parity kernels) — the "
+                         "fp32 line separates the view-batch restructuring from the precision / tensor-core share of the speed-up")
     ap.add_argument("--check", action="store_true", help="one eager step: loss / gradient / parameter-delta checksums (see run_check)")
     ap.add_argument("--check-against", default=None, help="gpurun_out/check_n1.pt of the 1-GPU --check run to compare with")
     args = ap.parse_args()
@@ -490,7 +493,7 @@ def main():
             _exit_multi_rank()
         return
     n_views, n_gauss = (24, 500000) if args.config == 5 else (N_VIEWS, P_GAUSS)
-    wl = ProductWorkload(rank, world, device, P=n_gauss, n_views=n_views)
+    wl = ProductWorkload(rank, world, device, P=n_gauss, n_views=n_views, dtype=torch.bfloat16 if args.dtype == "bf16" else torch.float32)
     if not args.no_graph:
         wl.capture()
     for _ in range(args.warmup):
@@ -543,10 +546,11 @@ def main():
     out = {
         "metric": METRIC if args.config == 4 else "rendered views/sec fwd+bwd @500k Gaussians, 1024x1024, 24 cams", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16 (StyleUNet) + fp32 (LBS, rasterizer)", "data": "synthetic",
+        "dtype": ("bf16 (StyleUNet) + fp32 (LBS, rasterizer)" if args.dtype == "bf16" else "fp32 (StyleUNet on the CUDA-core parity kernels, LBS, rasterizer)"),
+        "data": "synthetic",
         "config": {"workload": "BASELINE configs[%d]: train step fwd+bwd+Adam (loss head on the device: L1 image + L1 mask vs uint8 ground truth, "
                                "depth term, offset regulariser), synthetic %dk-Gaussian capsule avatar, 1 pose x %d views @1024x1024, "
-                               "bf16 StyleUNet, view-sharded over %d GPU(s)" % (args.config - 1, wl.P // 1000, n_views, world),
+                               "%s StyleUNet, view-sharded over %d GPU(s)" % (args.config - 1, wl.P // 1000, n_views, args.dtype, world),
                    "gaussians": wl.P, "views_per_step": n_views, "views_per_rank": len(wl.views), "image": [IMG, IMG],
                    "parallelism": "view-shard x%d + 1 all-reduce" % world, "cuda_graph": not args.no_graph,
                    "tile_instances_per_step": instances,

@@ -66,6 +66,11 @@ int agr_conv2d_forward(int32_t dtype, const AgrConvGeom* g, const void* x, const
                        const AgrConvEpilogue* ep, void* cuda_stream);
 /* dx (N,H,W,Cin) = adjoint of the geometry applied to dy (N,OH,OW,Cout) with w_t[ci][ky][kx][co]. */
 int agr_conv2d_dgrad(int32_t dtype, const AgrConvGeom* g, const void* dy, const void* w_t, void* dx, void* cuda_stream);
+/* The same data gradient on path 1 straight from the layer's KRSC weight (no transposed copy: the tensor cores read it as
+ * an MN-major operand).  The weight holds w_cin_total >= g->Cin input channels per tap (0 = g->Cin); dx receives the
+ * g->Cin channels starting at w_cin_offset (multiple of 64).  AGR_ERR_INVALID_ARGUMENT when agr_conv2d_path(.., 1) != 1. */
+int agr_conv2d_dgrad_krsc(int32_t dtype, const AgrConvGeom* g, const void* dy, const void* w_krsc, int32_t w_cin_total,
+                          int32_t w_cin_offset, void* dx, void* cuda_stream);
 /* dw[co][ky][kx][ci_offset + ci] (fp32, rows of ci_total floats) = sum over pixels of dy x x.  zero_first != 0 clears
  * the (Cout,k,k,ci_total) buffer before accumulating; partial sums are added with fp32 reductions (order not fixed). */
 int agr_conv2d_wgrad(int32_t dtype, const AgrConvGeom* g, const void* x, const void* dy, float* dw, int32_t ci_total,
@@ -74,12 +79,13 @@ int agr_conv2d_wgrad(int32_t dtype, const AgrConvGeom* g, const void* x, const v
 int agr_weight_transpose(int32_t dtype, const void* w_krsc, void* w_out, int32_t Cout, int32_t Cin, int32_t ksize,
                          void* cuda_stream);
 /* Tuning / A-B switch of path 1's forward-form kernel (same results, different staging): 1 = one TMA box per tap
- * (conv_tc_kernel), 2 = tap groups sharing one haloed box, 3 = tap groups + CTA pairs (cta_group::2; the default, also
- * selectable with the environment variable AGR_CONV_TC).  Returns the generation now in force; 0 leaves it unchanged. */
+ * (conv_tc_kernel), 2 = tap groups sharing one haloed box, 3 = tap groups + CTA pairs (cta_group::2), 0 = chosen per layer
+ * shape from measurements (the default; also the environment variable AGR_CONV_TC).  Returns the setting in force. */
 int agr_conv2d_set_generation(int32_t generation);
-/* Tuning: number of CTAs path 1's weight-gradient kernel aims for when it splits the pixel range (split-K with fp32
- * reductions into dw; more CTAs = more parallelism but more reduction traffic).  Returns the value in force; <= 0 leaves it. */
-int agr_conv2d_set_wgrad_ctas(int32_t ctas);
+/* Tuning of path 1's weight-gradient kernel, which splits the pixel range over CTAs (split-K with fp32 reductions into
+ * dw): at most `max_ctas` CTAs, each contracting at least `min_boxes` 16x8-pixel boxes (more CTAs = more parallelism but
+ * more reduction traffic per useful FLOP).  Values <= 0 leave a setting unchanged; returns max_ctas in force. */
+int agr_conv2d_set_wgrad_split(int32_t max_ctas, int32_t min_boxes);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,9 @@
 """TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench's cpu_baseline): CPU restatement of the trainer's photometric loss
 terms, main_avatar.py:193-222, for ONE view; a view batch is the mean over its views (all terms are means over equally
-sized views).  Parity unpinned: the reference computes this inside Trainer.forward_one_pass, which cannot be imported
-here (its module pulls in packages this image lacks); the restatement below follows it line by line in torch."""
+sized views).  The reference computes this inside AvatarTrainer.forward_one_pass, whose module cannot be imported here
+(it pulls in packages this image lacks); the restatement below follows it line by line in torch and is PINNED by running that
+method's unmodified source (oracle/ref_source.py compiles it out of the installed reference copy) on the same inputs:
+tests/test_zz_loss_head.py::test_loss_oracle_pinned_by_reference_trainer_source (total, logged terms, gradients)."""
 import torch
 
 

@@ -84,3 +84,48 @@ def test_flat_adam_state_dict_is_torch_adam_layout():
         group["lr"] = optim.cosine_lr(5e-4, 400000, 800000)
     assert abs(flat.lr - 5e-4 * (0.5 * 0.95 + 0.05)) < 1e-12
     assert abs(optim.cosine_lr(5e-4, 0, 800000) - 5e-4) < 1e-15 and abs(optim.cosine_lr(5e-4, 800000, 800000) - 2.5e-5) < 1e-12
+
+
+# ---- OpenEXR position maps (dataset/dataset_mv_rgb.py:146-151) -----------------------------------------------------------
+def test_exr_reader_matches_opencv_golden():
+    """formats.read_exr vs what OpenCV — the reference's reader — decoded from the same files (fixtures written and read back
+    by tests/golden/make_exr_golden.py): FLOAT / HALF, NONE / RLE / ZIPS / ZIP, raw (incompressible) blocks, a ragged last
+    block, one channel.  Bit-exact."""
+    import os
+    import numpy as np
+    from animatablegaussians_b200 import formats
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = np.load(os.path.join(gold_dir, "exr_golden.npz"))
+    assert len(gold.files) >= 7
+    for k in gold.files:
+        got = formats.read_exr(os.path.join(gold_dir, "exr_%s.exr" % k))
+        assert got.dtype == np.float32 and got.shape == gold[k].shape, k
+        assert np.array_equal(got, gold[k]), k
+
+
+def test_exr_reader_matches_live_opencv(tmp_path):
+    import os
+    import numpy as np
+    import pytest
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    from animatablegaussians_b200 import formats
+    rng = np.random.default_rng(11)
+    img = (rng.normal(size=(64, 128, 3)) * (rng.random((64, 128, 1)) > 0.4)).astype(np.float32)
+    path = str(tmp_path / "00000000.exr")
+    if not cv2.imwrite(path, img):
+        pytest.skip("this OpenCV build cannot write OpenEXR")
+    ref = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert np.array_equal(formats.read_exr(path), ref)
+    # the dataset's split of the (H, 2H, 3) map into the (6, H, H) network input
+    want = np.concatenate([ref[:, :64], ref[:, 64:]], 2).transpose(2, 0, 1)
+    assert np.array_equal(formats.load_smpl_pos_map(path).numpy(), want)
+
+
+def test_exr_reader_rejects_what_it_cannot_read(tmp_path):
+    import pytest
+    from animatablegaussians_b200 import formats
+    p = tmp_path / "bad.exr"
+    p.write_bytes(b"not an exr file at all")
+    with pytest.raises(ValueError):
+        formats.read_exr(str(p))

@@ -88,6 +88,7 @@ def test_avatar_render_matches_stock_reference(built_lib, tmp_path):
              g_rgb=rng.normal(size=(img, img, 3)).astype(np.float32), g_mask=rng.normal(size=(img, img, 1)).astype(np.float32),
              g_offset=(rng.normal(size=(N, 3)) * 1e-2).astype(np.float32), **can)
     a = _run("reference", "avatar", inp, str(tmp_path / "a.npz"), state)
+    a2 = _run("reference", "avatar", inp, str(tmp_path / "a2.npz"), state)    # the reference against itself: its own noise floor
     b = _run("dropin", "avatar", inp, str(tmp_path / "b.npz"), state)
     assert int(a["missing"][0]) == 0 and int(a["n_state"][0]) == len(net.state_dict())      # state_dict round trip, strict
 
@@ -115,12 +116,20 @@ def test_avatar_render_matches_stock_reference(built_lib, tmp_path):
         assert _l2(get("mask_map"), a["mask_map"]) <= 1e-3, name + ":mask_map rel L2 %.3e" % _l2(get("mask_map"), a["mask_map"])
         util.assert_close_robust(name + ":rgb_map", get("rgb_map"), a["rgb_map"], 2e-3, outlier_frac=5e-3, outlier_tol=1e-1)
         util.assert_close_robust(name + ":mask_map", get("mask_map"), a["mask_map"], 2e-3, outlier_frac=5e-3, outlier_tol=1e-1)
-        errs = {}
+        errs, floors = {}, {}
         for k in ref_stock.GRAD_KEYS:
             gk = other["grad:" + k] if other is not None else named[k].grad.detach().cpu().numpy()
-            errs[k] = _l2(gk, a["grad:" + k])
-        print(name, "parameter-gradient rel L2 vs the stock reference:", {k: "%.2e" % v for k, v in errs.items()})
-        # whole-network gradients cross ~40 leaky-ReLU kinks -> relative L2 (see tests/test_styleunet.py::_check)
-        bad = {k: v for k, v in errs.items() if v > 2e-2}
-        assert not bad, "%s: %s" % (name, {k: "%.3e" % v for k, v in bad.items()})
+            errs[k], floors[k] = _l2(gk, a["grad:" + k]), _l2(a2["grad:" + k], a["grad:" + k])
+        print(name, "parameter-gradient rel L2 vs the stock reference (reference vs itself):",
+              {k: "%.2e (%.2e)" % (errs[k], floors[k]) for k in errs})
+        # Whole-network gradients cross ~40 leaky-ReLU kinks -> relative L2 (see tests/test_styleunet.py::_check).  The
+        # geometry gradients of the rasterizer (means / scales / rotations -> position_net, other_net) are heavy-tailed and
+        # the reference does not reproduce ITSELF on them from one run to the next (its U-Net forward differs by ~1e-7
+        # between runs, which a handful of ill-conditioned Gaussians amplify; tools/diag_stock.py prints the per-tensor
+        # numbers), so each key is held to the larger of 2e-2 and 3x the reference's own run-to-run distance.
+        bad = {k: v for k, v in errs.items() if v > max(2e-2, 3.0 * floors[k])}
+        assert not bad, "%s: %s" % (name, {k: "%.3e (floor %.3e)" % (v, floors[k]) for k, v in bad.items()})
+        # ... and the colour / view-direction path, which IS reproducible, must stay tight
+        tight = [k for k in errs if k.startswith(("color_net", "viewdir_net"))]
+        assert tight and all(errs[k] <= 2e-2 for k in tight)
     ops.set_compute_dtype(torch.float32)

@@ -45,3 +45,74 @@ def test_photometric_loss_matches_oracle(V, H, W, built_lib):
     assert abs(float(total) - float(l1_ref + 0.1 * mk_ref)) < 1e-5
     assert torch.allclose(rgb.grad.double().cpu(), r2.grad, rtol=1e-5, atol=1e-10)
     assert torch.allclose(alpha.grad.double().cpu(), a2.grad, rtol=1e-5, atol=1e-10)
+
+
+def test_crop_image_matches_reference_source():
+    """loss.crop_image vs the reference's own `AvatarTrainer.crop_image` (main_avatar.py:75-115), whose unmodified source is
+    compiled by oracle/ref_source.py: resize branch and random-window branch (same torch RNG stream), tall and wide boxes."""
+    import types
+    import torch.nn.functional as F
+    from animatablegaussians_b200 import loss
+    from oracle import ref_source
+    ref = ref_source.method("main_avatar.py", "AvatarTrainer", "crop_image", {"torch": torch, "F": F})
+    if ref is None:
+        pytest.skip("reference source not present (baseline/_ref or /root/reference)")
+    g = torch.Generator().manual_seed(3)
+    for (H, W, box, patch, randomly) in [(96, 80, (10, 70, 20, 50), 32, False), (96, 80, (30, 50, 5, 75), 32, False),
+                                         (128, 128, (8, 120, 30, 100), 48, True), (64, 64, (10, 30, 12, 28), 48, True)]:
+        mask = torch.zeros(H, W)
+        mask[box[0]:box[1], box[2]:box[3]] = (torch.rand(box[1] - box[0], box[3] - box[2], generator=g) > 0.3).float()
+        mask[box[0], box[2]] = mask[box[1] - 1, box[3] - 1] = 1.0
+        a, b = torch.rand(3, H, W, generator=g), torch.rand(3, H, W, generator=g)
+        bg = torch.tensor([0.1, 0.5, 0.9])
+        me = types.SimpleNamespace(bg_color_cuda=bg)
+        torch.manual_seed(17)
+        want = ref(me, mask, patch, randomly, a, b)
+        torch.manual_seed(17)
+        got = loss.crop_image(mask, patch, randomly, a, b, bg_color=bg)
+        assert len(got) == 2
+        for x, y in zip(got, want):
+            assert x.shape == y.shape == (3, patch, patch) and torch.equal(x, y)
+    torch.manual_seed(17)
+    one = loss.crop_image(mask, 48, True, a, bg_color=bg)
+    assert isinstance(one, torch.Tensor)
+
+
+def test_loss_oracle_pinned_by_reference_trainer_source():
+    """oracle/loss_oracle.photometric_terms (the checker of the fused loss kernel) against the reference trainer's OWN
+    `AvatarTrainer.forward_one_pass` (main_avatar.py:166-264), compiled unmodified by oracle/ref_source.py and run on CPU with
+    a stub `self` whose avatar_net.render returns given maps: total loss, logged terms and the gradients it back-propagates."""
+    import types
+    import numpy as np
+    from oracle import loss_oracle as lo, ref_source
+    ns = {"torch": torch, "np": np, "config": types.SimpleNamespace(device="cpu"),
+          "net_util": types.SimpleNamespace(delete_batch_idx=lambda d: d)}
+    fwd = ref_source.method("main_avatar.py", "AvatarTrainer", "forward_one_pass", ns)
+    if fwd is None:
+        pytest.skip("reference source not present (baseline/_ref or /root/reference)")
+    g = torch.Generator().manual_seed(5)
+    H, W, N = 40, 56, 300
+    for bgc in ((0., 0., 0.), (1.0, 0.5, 0.25)):
+        rgb = torch.rand(H, W, 3, generator=g).requires_grad_(True)
+        alpha = torch.rand(H, W, 1, generator=g).requires_grad_(True)
+        offset = (torch.randn(N, 3, generator=g) * 0.01).requires_grad_(True)
+        gt = torch.rand(H, W, 3, generator=g)
+        mask = torch.rand(H, W, generator=g) > 0.4
+        boundary = torch.rand(H, W, generator=g) > 0.9
+        bg = torch.tensor(bgc)
+        noop = types.SimpleNamespace(step=lambda: None, zero_grad=lambda: None)
+        me = types.SimpleNamespace(random_bg_color=False, bg_color=bgc, bg_color_cuda=bg, finetune_color=False,
+                                   requires_net_grad=lambda *a: None, optm=noop, iter_idx=0, patch_size=32,
+                                   loss_weight={"l1": 1.0, "mask": 0.1, "lpips": 0.0, "offset": 0.005},
+                                   avatar_net=types.SimpleNamespace(render=lambda items, bg_color: {"rgb_map": rgb, "mask_map": alpha, "offset": offset}))
+        items = {"color_img": gt.clone(), "mask_img": mask.clone(), "boundary_mask_img": boundary.clone()}
+        total_ref, logged = fwd(me, items)
+        want = (rgb.grad.clone(), alpha.grad.clone(), offset.grad.clone())
+        rgb.grad = alpha.grad = offset.grad = None
+        l1, mk = lo.photometric_terms(rgb, alpha, gt, mask, boundary, bg)
+        total = 1.0 * l1 + 0.1 * mk + 0.005 * torch.linalg.norm(offset, dim=-1).mean()
+        total.backward()
+        assert abs(float(total) - float(total_ref)) < 1e-7
+        assert abs(float(l1) - logged["l1_loss"]) < 1e-7 and abs(float(mk) - logged["mask_loss"]) < 1e-7
+        for got, w in zip((rgb.grad, alpha.grad, offset.grad), want):
+            assert torch.allclose(got, w, rtol=1e-6, atol=1e-9)

@@ -36,10 +36,10 @@ def dev_ms(fn, n=20):
 
 
 def main():
-    gens = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1,2,3").split(",")]
+    gens = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1,2,3,0").split(",")]
     lib = _lib.load()
-    wg = [int(v) for v in os.environ.get("WGRAD_CTAS", "296").split(",")]
-    print("%-44s" % "geometry" + "".join("  fwd g%d  TF/s | dgrad g%d  TF/s |" % (g, g) for g in gens) + "".join("  wgrad@%d TF/s |" % c for c in wg))
+    wg = [tuple(int(u) for u in v.split(":")) for v in os.environ.get("WGRAD_SPLIT", "296:16").split(",")]   # max_ctas:min_boxes
+    print("%-44s" % "geometry" + "".join("  fwd g%d  TF/s | dgrad g%d  TF/s |" % (g, g) for g in gens) + "".join("  wg@%d:%d TF/s |" % c for c in wg))
     tot = {g: [0.0, 0.0] for g in gens}
     totw = {}
     for (N, H, W, Cin, Cout, k, st, pad, T) in SHAPES:
@@ -53,19 +53,19 @@ def main():
         for gen in gens:
             lib.agr_conv2d_set_generation(gen)
             a = dev_ms(lambda: ops.conv_forward(x, w, g))
-            b = dev_ms(lambda: ops.conv_dgrad(dy, wt, g))
+            b = dev_ms(lambda: ops.conv_dgrad_w(dy, w, g))
             tot[gen][0] += a; tot[gen][1] += b
             line += " %7.3f %5.0f | %8.3f %5.0f |" % (a, fl / a / 1e9, b, fl / b / 1e9)
         for c_ in wg:
-            lib.agr_conv2d_set_wgrad_ctas(c_)
+            lib.agr_conv2d_set_wgrad_split(*c_)
             c = dev_ms(lambda: ops.conv_wgrad(x, dy, g))
             totw[c_] = totw.get(c_, 0.0) + c
             line += " %7.3f %5.0f |" % (c, fl / c / 1e9)
-        lib.agr_conv2d_set_wgrad_ctas(296)
+        lib.agr_conv2d_set_wgrad_split(296, 16)
         print(line, flush=True)
         del x, w, dy, wt
     print("sum ms: " + "  ".join("g%d fwd %.3f dgrad %.3f" % (g, tot[g][0], tot[g][1]) for g in gens) + "  wgrad " + str({k: round(v, 3) for k, v in totw.items()}))
-    lib.agr_conv2d_set_generation(3)
+    lib.agr_conv2d_set_generation(0)
 
 
 if __name__ == "__main__":

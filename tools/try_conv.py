@@ -39,15 +39,21 @@ def case(N, H, W, Cin, Cout, k, stride, pad, transposed, dtype, time_it=False):
     dy = torch.randn(yr.shape, device="cuda", generator=g).to(dtype).contiguous(memory_format=CL)
     yr.backward(dy.float())
     dx = ops.conv_dgrad(dy, ops.weight_transpose(w), geom)
+    dx2 = ops.conv_dgrad_w(dy, w, geom)            # tensor-core path: straight from the KRSC operand (MN-major B)
+    if Cin % 128 == 0 and paths[1] == 1:           # ... and a slice of the weight's input channels (split contraction)
+        gh = ops.conv_geom((N, Cin // 2, H, W), Cout, k, stride, pad, transposed)
+        dxh = ops.conv_dgrad_w(dy, w, gh, Cin, Cin // 2)
+    else:
+        dxh = None
     dw = ops._as_kcrs(ops.conv_wgrad(x, dy, geom))
     torch.cuda.synchronize()
-    e = (rel(y, yr), rel(dx, xr.grad), rel(dw, wr.grad))
+    e = (rel(y, yr), max(rel(dx, xr.grad), rel(dx2, xr.grad), 0.0 if dxh is None else rel(dxh, xr.grad[:, Cin // 2:])), rel(dw, wr.grad))
     tol = 2e-2 if dtype == torch.bfloat16 else 2e-5
     msg = "%-4s N%-2d %3dx%-3d %4d->%-4d k%d s%d p%d %s paths %s  fwd %.1e dgrad %.1e wgrad %.1e" % (
         "bf16" if dtype == torch.bfloat16 else "fp32", N, H, W, Cin, Cout, k, stride, pad, "T" if transposed else " ", paths, *e)
     if time_it:
         fl = ops._flops(geom)
-        for name, fn in (("fwd", lambda: ops.conv_forward(x, w, geom)), ("dgrad", lambda: ops.conv_dgrad(dy, ops.weight_transpose(w), geom)),
+        for name, fn in (("fwd", lambda: ops.conv_forward(x, w, geom)), ("dgrad", lambda: ops.conv_dgrad_w(dy, w, geom)),
                          ("wgrad", lambda: ops.conv_wgrad(x, dy, geom))):
             for _ in range(3):
                 fn()
@@ -75,7 +81,8 @@ GROUPS = {
                (1, 16, 16, 512, 32, 1, 1, 0, False)],
     "big": [(16, 512, 512, 64, 64, 3, 1, 1, False), (16, 256, 256, 128, 64, 3, 2, 0, True), (16, 256, 256, 256, 128, 3, 1, 1, False),
             (1, 129, 129, 256, 512, 3, 2, 0, False), (1, 64, 64, 1024, 512, 3, 1, 1, False), (16, 512, 512, 64, 12, 1, 1, 0, False),
-            (32, 256, 256, 64, 128, 4, 2, 1, False)],
+            (32, 256, 256, 64, 128, 4, 2, 1, False), (1, 512, 512, 64, 64, 3, 1, 1, False), (3, 200, 328, 64, 64, 3, 1, 1, False),
+            (2, 200, 168, 128, 64, 3, 2, 0, True), (1, 256, 256, 256, 128, 3, 1, 1, False), (1, 128, 128, 512, 256, 3, 1, 1, False)],
 }
 
 if __name__ == "__main__":
