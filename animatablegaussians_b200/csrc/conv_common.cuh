@@ -145,6 +145,133 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// ---- warp-uniform issue ---------------------------------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / cp.async.bulk.tensor are issued by ONE thread, but the loop around them should be run by the
+// WHOLE warp with the asynchronous instruction predicated on an elect.sync flag: inside `if (lane == 0) { ... }` ptxas cannot
+// prove the operands warp-uniform, keeps descriptors and loop counters in vector registers and wraps every UTCHMMA / UTMALDG
+// in an ELECT + R2UR + BRA.U.ANY "waterfall" (~20 instructions and a dependent chain per MMA: measured 190 cycles per
+// 128x64x16 MMA whose tensor time is 32 cycles — profiles/r02_ncu_conv64*.txt).  Convergent code keeps everything in uniform
+// registers and the MMAs issue back to back.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+constexpr uint32_t UMMA_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B (bits 32..63)
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ void umma_f16_p(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t el) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "mov.b64 da, {%1, %6};\n\tmov.b64 db, {%2, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(el), "r"(UMMA_DESC_HI) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair_p(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t el) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "mov.b64 da, {%1, %6};\n\tmov.b64 db, {%2, %6};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(el), "r"(UMMA_DESC_HI) : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(el) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_p(uint64_t* bar, uint32_t el) {   // arrives at this offset in BOTH CTAs of the pair
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(el), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint64_t* bar, uint32_t bytes, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(bytes), "r"(el) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_p(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+                 "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(el) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_p(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+                 "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(el) : "memory");
+}
+// CTA-pair forms: the data lands in the issuing CTA's shared memory, the bytes are counted on the barrier `bar` (a
+// shared::cluster address, normally the leader CTA's)
+__device__ __forceinline__ void tma_load_4d_pair_p(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+                 "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(el) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair_p(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+                 "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(el) : "memory");
+}
+// ---- epilogue of the forward-form kernels: one accumulator row (TMEM lane) per thread, BN columns in chunks of 32 ----------
+//   y = act(acc + residual + noise + bias) -> bf16, or the raw fp32 accumulator (out32).  Launches without any of that (every
+//   data gradient) take the `plain` path: tcgen05.ld, 16 packs, 4 x 16-byte stores per chunk.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_row(uint32_t taddr, bool valid, const float* __restrict__ bias, const float* __restrict__ res,
+                                                  float* __restrict__ out32, __nv_bfloat16* __restrict__ out, float add, bool has_noise, int activate) {
+    const bool plain = !bias && !res && !out32 && !activate && !has_noise;
+    const float gain = activate == 1 ? 1.4142135623730951f : 1.f, neg_slope = activate == 3 ? 0.f : 0.2f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_wait_ld();
+        if (!valid) continue;
+        uint4 packed[4];
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(packed);
+        if (plain) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) h2[i] = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+        } else {
+            if (res) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 rr = __ldg(reinterpret_cast<const float4*>(res + c0) + i);
+                    r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + rr.x);
+                    r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + rr.y);
+                    r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + rr.z);
+                    r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + rr.w);
+                }
+            }
+            if (out32) {   // fp32 partial result (no epilogue math): consumed as `residual` by the second half of a split contraction
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    reinterpret_cast<float4*>(out32 + c0)[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                                           __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                continue;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 b = make_float4(add, add, add, add);
+                if (bias) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + i);
+                    b.x += bb.x; b.y += bb.y; b.z += bb.z; b.w += bb.w;
+                }
+                float v0 = __uint_as_float(r[4 * i]) + b.x, v1 = __uint_as_float(r[4 * i + 1]) + b.y;
+                float v2 = __uint_as_float(r[4 * i + 2]) + b.z, v3 = __uint_as_float(r[4 * i + 3]) + b.w;
+                if (activate) {
+                    v0 = (v0 > 0.f ? v0 : neg_slope * v0) * gain; v1 = (v1 > 0.f ? v1 : neg_slope * v1) * gain;
+                    v2 = (v2 > 0.f ? v2 : neg_slope * v2) * gain; v3 = (v3 > 0.f ? v3 : neg_slope * v3) * gain;
+                }
+                h2[2 * i] = __floats2bfloat162_rn(v0, v1);
+                h2[2 * i + 1] = __floats2bfloat162_rn(v2, v3);
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = packed[i];
+    }
+}
+
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(COLS) : "memory");

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectParams p) 
     // epilogue
     TO* y = static_cast<TO*>(p.y);
     const float nw = (p.noise && p.noise_w) ? p.noise_w[0] : 0.f;
-    const float gain = p.activate == 1 ? 1.4142135623730951f : 1.f;
+    const float gain = p.activate == 1 ? 1.4142135623730951f : 1.f, neg_slope = p.activate == 3 ? 0.f : 0.2f;
     const long plane = (long)p.OH * p.OW;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectParams p) 
             const int co = co0 + tx * CN + j;
             if (co >= p.Cout) continue;
             float v = acc[i][j] + add + (p.bias ? p.bias[co] : 0.f);
-            if (p.activate) v = (v > 0.f ? v : 0.2f * v) * gain;
+            if (p.activate) v = (v > 0.f ? v : neg_slope * v) * gain;
             stf(y + P * p.Cout + co, v);
         }
     }
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) pw12_fwd_kernel(const PwParams p) {
     const T* x = static_cast<const T*>(p.x);
     T* y = static_cast<T*>(p.y);
     const float nw = (p.noise && p.noise_w) ? p.noise_w[0] : 0.f;
-    const float gain = p.activate == 1 ? 1.4142135623730951f : 1.f;
+    const float gain = p.activate == 1 ? 1.4142135623730951f : 1.f, neg_slope = p.activate == 3 ? 0.f : 0.2f;
     // the output channel this lane ends up holding after the halving butterfly (+ co_b = its pair's third value)
     const int co_a = 6 * ((c >> 2) & 1) + 3 * ((c >> 1) & 1) + (c & 1), co_b = 6 * ((c >> 2) & 1) + 3 * ((c >> 1) & 1) + 2;
     for (long p4 = ((long)blockIdx.x * 8 + warp) * 4; p4 < p.pixels; p4 += (long)gridDim.x * 32) {
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256) pw12_fwd_kernel(const PwParams p) {
             const float add = p.noise ? nw * p.noise[px % p.plane] : 0.f;
             ra += add + (p.bias ? p.bias[co_a] : 0.f);
             rb += add + (p.bias ? p.bias[co_b] : 0.f);
-            if (p.activate) { ra = (ra > 0.f ? ra : 0.2f * ra) * gain; rb = (rb > 0.f ? rb : 0.2f * rb) * gain; }
+            if (p.activate) { ra = (ra > 0.f ? ra : neg_slope * ra) * gain; rb = (rb > 0.f ? rb : neg_slope * rb) * gain; }
             stf(y + px * PW + co_a, ra);
             if (!(c & 1)) stf(y + px * PW + co_b, rb);
         }
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(256) pw12_fwd_mma_kernel(const PwParams p) {
     const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(p.w);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(p.y);
     const float nw = (p.noise && p.noise_w) ? p.noise_w[0] : 0.f;
-    const float gain = p.activate == 1 ? 1.4142135623730951f : 1.f;
+    const float gain = p.activate == 1 ? 1.4142135623730951f : 1.f, neg_slope = p.activate == 3 ? 0.f : 0.2f;
     const int slabs = p.Cin / 64;
     uint4 wq[2][2];   // [n-tile][half]: weights of output gid (+8) for this lane's 16 channels (slab 0 kept in registers)
     auto load_w = [&](int slab) {
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(256) pw12_fwd_mma_kernel(const PwParams p) {
         }
         auto fin = [&](float v, float b, long px) {
             v += b + (p.noise ? nw * p.noise[px % p.plane] : 0.f);
-            if (p.activate) v = (v > 0.f ? v : 0.2f * v) * gain;
+            if (p.activate) v = (v > 0.f ? v : neg_slope * v) * gain;
             return v;
         };
         if (v0) {

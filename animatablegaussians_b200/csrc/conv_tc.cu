@@ -91,46 +91,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
-        // ================= TMA producer (one elected lane) =================
-        if (lane == 0) {
-            for (int it = 0; it < num_kb; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                const int tap = t_begin + it / kchunks, ck = it % kchunks;
-                unsigned char* a_dst = smem + s * STAGE_BYTES;
-                unsigned char* b_dst = a_dst + A_BYTES;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                // OOB -> zeros = padding; with in_stride 2 the box holds every other pixel from its origin
-                tma_load_4d(a_dst, &map_x, &full_bar[s], ck * BK, p.in_stride * w0 + p.taps.dx[tap], p.in_stride * h0 + p.taps.dy[tap], img);
-                if (B_MN) {
+        // ================= TMA producer: the whole warp runs the loop, the copies are predicated on one elected lane =================
+        const uint32_t el = elect_one();
+        const uint32_t smem_base = smem_u32(smem);
+        for (int it = 0; it < num_kb; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const int tap = t_begin + it / kchunks, ck = it % kchunks;
+            const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+            const uint32_t b_dst = a_dst + A_BYTES;
+            const uint32_t bar = smem_u32(&full_bar[s]);
+            mbar_expect_tx_p(&full_bar[s], STAGE_BYTES, el);
+            // OOB -> zeros = padding; with in_stride 2 the box holds every other pixel from its origin
+            tma_load_4d_p(a_dst, &map_x, bar, ck * BK, p.in_stride * w0 + p.taps.dx[tap], p.in_stride * h0 + p.taps.dy[tap], img, el);
+            if (B_MN) {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j)
-                        tma_load_3d(b_dst + j * (64 * BK * 2), &map_w, &full_bar[s], p.w_cin_offset + n0 + 64 * j, p.taps.wt[tap], ck * BK);
-                } else {
-                    tma_load_3d(b_dst, &map_w, &full_bar[s], p.w_cin_offset + ck * BK, p.taps.wt[tap], n0);
-                }
+                for (int j = 0; j < BN / 64; ++j)
+                    tma_load_3d_p(b_dst + j * (64 * BK * 2), &map_w, bar, p.w_cin_offset + n0 + 64 * j, p.taps.wt[tap], ck * BK, el);
+            } else {
+                tma_load_3d_p(b_dst, &map_w, bar, p.w_cin_offset + ck * BK, p.taps.wt[tap], n0, el);
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one elected lane) =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc2(BM, BN, 0, B_MN ? 1 : 0);
-            for (int it = 0; it < num_kb; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + A_BYTES;
-                const uint64_t adesc = umma_desc(a_addr, 16), bdesc = umma_desc(b_addr, B_MN ? 64 * BK * 2 : 16);
+        // ================= MMA issuer: convergent loop, tcgen05.mma / commit predicated on one elected lane =================
+        const uint32_t el = elect_one();
+        const uint32_t idesc = umma_idesc2(BM, BN, 0, B_MN ? 1 : 0);
+        const uint32_t smem_base = smem_u32(smem);
+        for (int it = 0; it < num_kb; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_lo = umma_desc_lo(smem_base + s * STAGE_BYTES, 16);
+            const uint32_t b_lo = umma_desc_lo(smem_base + s * STAGE_BYTES + A_BYTES, B_MN ? 64 * BK * 2 : 16);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16: +32 B along a K-major row, +16 rows (2048 B) of an MN-major tile
-                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc, (it | k) != 0 ? 1u : 0u);
-                umma_commit(&empty_bar[s]);      // frees the smem stage once these MMAs have read it
-            }
-            umma_commit(&tmem_full_bar);         // accumulator complete
+            for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16: +32 B along a K-major row, +16 rows (2048 B) of an MN-major tile
+                umma_f16_p(tmem_base, a_lo + 2 * k, b_lo + (B_MN ? 128 : 2) * k, idesc, (it | k) != 0 ? 1u : 0u, el);
+            umma_commit_p(&empty_bar[s], el);      // frees the smem stage once these MMAs have read it
         }
+        umma_commit_p(&tmem_full_bar, el);         // accumulator complete
     } else {
         // ================= epilogue: TMEM -> registers -> (+residual, +noise, +bias, lrelu) -> global =================
         mbar_wait(&tmem_full_bar, 0);
@@ -146,46 +146,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         __nv_bfloat16* out = p.y + opix * p.Cout + n0;
         const float* res = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
         float* out32 = p.y_f32 ? p.y_f32 + opix * p.Cout + n0 : nullptr;
-        const float slope_gain = p.activate == 1 ? 1.4142135623730951f : 1.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            tmem_wait_ld();
-            if (!valid) continue;
-            if (res) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 rr = reinterpret_cast<const float4*>(res + c0)[i];
-                    r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + rr.x);
-                    r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + rr.y);
-                    r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + rr.z);
-                    r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + rr.w);
-                }
-            }
-            if (out32) {   // fp32 partial result (no epilogue math): consumed as `residual` by the second half
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    reinterpret_cast<float4*>(out32 + c0)[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                                           __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                continue;
-            }
-            uint4 packed[4];
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(packed);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float v0 = __uint_as_float(r[2 * i]) + add, v1 = __uint_as_float(r[2 * i + 1]) + add;
-                if (p.bias) { v0 += p.bias[n0 + c0 + 2 * i]; v1 += p.bias[n0 + c0 + 2 * i + 1]; }
-                if (p.activate) {
-                    v0 = (v0 > 0.f ? v0 : 0.2f * v0) * slope_gain;
-                    v1 = (v1 > 0.f ? v1 : 0.2f * v1) * slope_gain;
-                }
-                h2[i] = __floats2bfloat162_rn(v0, v1);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(out + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = packed[i];
-        }
+        conv_epilogue_row<BN>(tmem_base + ((uint32_t)(q * 32) << 16), valid, p.bias ? p.bias + n0 : nullptr, res, out32, out, add,
+                              p.noise != nullptr && p.noise_w != nullptr, p.activate);
         tc_fence_before();
     }
     __syncthreads();
@@ -256,48 +218,51 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
-            const int sx = p.x_shifted ? p.stride : 1, sy = p.x_shifted ? 1 : p.stride;
-            const int xdx = p.x_shifted ? grp.dx : 0, xdy = p.x_shifted ? grp.dy : 0;
-            const int ydx = p.x_shifted ? 0 : grp.dx, ydy = p.x_shifted ? 0 : grp.dy;
-            int s = 0; uint32_t ph = 0;
-            for (int it = 0; it < num_kb; ++it) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                const int b = box0 + it;
-                const int img = b / boxes_img, t = b - img * boxes_img;
-                const int h0 = (t / tiles_w) * TILE_H, w0 = (t % tiles_w) * TILE_W;
-                unsigned char* a_dst = smem + s * stage_bytes;
-                unsigned char* b_dst = a_dst + a_bytes;
-                mbar_expect_tx(&full_bar[s], stage_bytes);
+        // producer: convergent loop, copies predicated on one elected lane (see conv_common.cuh "warp-uniform issue")
+        const uint32_t el = elect_one();
+        const uint32_t smem_base = smem_u32(smem);
+        const int sx = p.x_shifted ? p.stride : 1, sy = p.x_shifted ? 1 : p.stride;
+        const int xdx = p.x_shifted ? grp.dx : 0, xdy = p.x_shifted ? grp.dy : 0;
+        const int ydx = p.x_shifted ? 0 : grp.dx, ydy = p.x_shifted ? 0 : grp.dy;
+        int s = 0; uint32_t ph = 0;
+        for (int it = 0; it < num_kb; ++it) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const int b = box0 + it;
+            const int img = b / boxes_img, t = b - img * boxes_img;
+            const int h0 = (t / tiles_w) * TILE_H, w0 = (t % tiles_w) * TILE_W;
+            const uint32_t a_dst = smem_base + s * stage_bytes;
+            const uint32_t b_dst = a_dst + a_bytes;
+            const uint32_t bar = smem_u32(&full_bar[s]);
+            mbar_expect_tx_p(&full_bar[s], stage_bytes, el);
 #pragma unroll
-                for (int j = 0; j < MT / 64; ++j) tma_load_4d(a_dst + j * a_box, &map_x, &full_bar[s], ci0 + 64 * j, sx * w0 + xdx, sx * h0 + xdy, img);
+            for (int j = 0; j < MT / 64; ++j) tma_load_4d_p(a_dst + j * a_box, &map_x, bar, ci0 + 64 * j, sx * w0 + xdx, sx * h0 + xdy, img, el);
 #pragma unroll
-                for (int j = 0; j < NT / 64; ++j) tma_load_4d(b_dst + j * b_box, &map_dy, &full_bar[s], co0 + 64 * j, sy * w0 + ydx, sy * h0 + ydy, img);
-                if (++s == STAGES) { s = 0; ph ^= 1; }
-            }
+            for (int j = 0; j < NT / 64; ++j) tma_load_4d_p(b_dst + j * b_box, &map_dy, bar, co0 + 64 * j, sy * w0 + ydx, sy * h0 + ydy, img, el);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(MT, NT, 1);   // a_major = b_major = MN
-            int s = 0; uint32_t ph = 0;
-            for (int it = 0; it < num_kb; ++it) {
-                mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-                const uint32_t b_addr = a_addr + a_bytes;
-                for (int t = 0; t < grp.ntaps; ++t) {
-                    const uint32_t a_t = a_addr + (p.x_shifted ? grp.r[t] * ROW_BYTES : 0);
-                    const uint32_t b_t = b_addr + (p.x_shifted ? 0 : grp.r[t] * ROW_BYTES);
+        const uint32_t el = elect_one();
+        const uint32_t idesc = umma_idesc(MT, NT, 1);   // a_major = b_major = MN
+        const uint32_t smem_base = smem_u32(smem);
+        int s = 0; uint32_t ph = 0;
+        uint32_t acc = 0;
+        for (int it = 0; it < num_kb; ++it) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + s * stage_bytes;
+            const uint32_t b_addr = a_addr + a_bytes;
+            for (int t = 0; t < grp.ntaps; ++t) {
+                const uint32_t a_lo = umma_desc_lo(a_addr + (p.x_shifted ? grp.r[t] * ROW_BYTES : 0), a_box);
+                const uint32_t b_lo = umma_desc_lo(b_addr + (p.x_shifted ? 0 : grp.r[t] * ROW_BYTES), b_box);
 #pragma unroll
-                    for (int k = 0; k < BM / 16; ++k)   // 16 pixels per MMA = two 8-row groups = 2048 B
-                        umma_f16(tmem_base + t * NT, umma_desc(a_t + k * ROW_BYTES, a_box), umma_desc(b_t + k * ROW_BYTES, b_box), idesc,
-                                 (it | k) != 0 ? 1u : 0u);
-                }
-                umma_commit(&empty_bar[s]);
-                if (++s == STAGES) { s = 0; ph ^= 1; }
+                for (int k = 0; k < BM / 16; ++k)   // 16 pixels per MMA = two 8-row groups = 2048 B = +128 in the (>>4) address field
+                    umma_f16_p(tmem_base + t * NT, a_lo + 128 * k, b_lo + 128 * k, idesc, (acc | (uint32_t)k) != 0 ? 1u : 0u, el);
             }
-            umma_commit(&tmem_full_bar);
+            acc = 1;
+            umma_commit_p(&empty_bar[s], el);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        umma_commit_p(&tmem_full_bar, el);
     } else {
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();

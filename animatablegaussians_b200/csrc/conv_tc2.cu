@@ -146,71 +146,74 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
-        // ================= TMA producer (one elected lane of EACH CTA) =================
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int it = 0; it < num_it; ++it) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                const TapGroup grp = p.groups[g_begin + it / kchunks];
-                const int ck = it % kchunks;
-                unsigned char* a_dst = smem + s * STAGE_BYTES;
-                unsigned char* b_dst = a_dst + A_SLOT;
-                const int x0 = p.in_stride * w0 + grp.dx, y0 = p.in_stride * h0 + grp.dy;
-                if (PAIR) {
-                    // both CTAs' bytes are counted on the leader's barrier; the leader alone arrives on it
-                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)(a_bytes + grp.ntaps * B_BYTES));
-                    const uint32_t bar = mapa_rank0(smem_u32(&full_bar[s]));
-                    tma_load_4d_pair(a_dst, &map_x, bar, ck * BK, x0, y0, img);
-                    for (int t = 0; t < grp.ntaps; ++t) {
-                        if (B_MN) {
+        // ================= TMA producer of EACH CTA: convergent loop, copies predicated on one elected lane =================
+        const uint32_t el = elect_one();
+        const uint32_t smem_base = smem_u32(smem);
+        int s = 0; uint32_t ph = 0;
+        for (int it = 0; it < num_it; ++it) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const TapGroup grp = p.groups[g_begin + it / kchunks];
+            const int ck = it % kchunks;
+            const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+            const uint32_t b_dst = a_dst + A_SLOT;
+            const int x0 = p.in_stride * w0 + grp.dx, y0 = p.in_stride * h0 + grp.dy;
+            if (PAIR) {
+                // both CTAs' bytes are counted on the leader's barrier; the leader alone arrives on it
+                mbar_expect_tx_p(&full_bar[s], 2u * (uint32_t)(a_bytes + grp.ntaps * B_BYTES), rank == 0 ? el : 0u);
+                const uint32_t bar = mapa_rank0(smem_u32(&full_bar[s]));
+                tma_load_4d_pair_p(a_dst, &map_x, bar, ck * BK, x0, y0, img, el);
+                for (int t = 0; t < grp.ntaps; ++t) {
+                    if (B_MN) {
 #pragma unroll
-                            for (int j = 0; j < BNL / 64; ++j)
-                                tma_load_3d_pair(b_dst + t * B_BYTES + j * (64 * BK * 2), &map_w, bar, p.w_cin_offset + n0 + (int)rank * BNL + 64 * j, grp.wt[t], ck * BK);
-                        } else {
-                            tma_load_3d_pair(b_dst + t * B_BYTES, &map_w, bar, p.w_cin_offset + ck * BK, grp.wt[t], n0 + (int)rank * BNL);
-                        }
-                    }
-                } else {
-                    mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + grp.ntaps * B_BYTES));
-                    tma_load_4d(a_dst, &map_x, &full_bar[s], ck * BK, x0, y0, img);
-                    for (int t = 0; t < grp.ntaps; ++t) {
-                        if (B_MN) {
-#pragma unroll
-                            for (int j = 0; j < BNL / 64; ++j)
-                                tma_load_3d(b_dst + t * B_BYTES + j * (64 * BK * 2), &map_w, &full_bar[s], p.w_cin_offset + n0 + 64 * j, grp.wt[t], ck * BK);
-                        } else {
-                            tma_load_3d(b_dst + t * B_BYTES, &map_w, &full_bar[s], p.w_cin_offset + ck * BK, grp.wt[t], n0);
-                        }
+                        for (int j = 0; j < BNL / 64; ++j)
+                            tma_load_3d_pair_p(b_dst + t * B_BYTES + j * (64 * BK * 2), &map_w, bar, p.w_cin_offset + n0 + (int)rank * BNL + 64 * j, grp.wt[t], ck * BK, el);
+                    } else {
+                        tma_load_3d_pair_p(b_dst + t * B_BYTES, &map_w, bar, p.w_cin_offset + ck * BK, grp.wt[t], n0 + (int)rank * BNL, el);
                     }
                 }
-                if (++s == STAGES) { s = 0; ph ^= 1; }
+            } else {
+                const uint32_t bar = smem_u32(&full_bar[s]);
+                mbar_expect_tx_p(&full_bar[s], (uint32_t)(a_bytes + grp.ntaps * B_BYTES), el);
+                tma_load_4d_p(a_dst, &map_x, bar, ck * BK, x0, y0, img, el);
+                for (int t = 0; t < grp.ntaps; ++t) {
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BNL / 64; ++j)
+                            tma_load_3d_p(b_dst + t * B_BYTES + j * (64 * BK * 2), &map_w, bar, p.w_cin_offset + n0 + 64 * j, grp.wt[t], ck * BK, el);
+                    } else {
+                        tma_load_3d_p(b_dst + t * B_BYTES, &map_w, bar, p.w_cin_offset + ck * BK, grp.wt[t], n0, el);
+                    }
+                }
             }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one elected lane; in pair mode of the leader CTA only) =================
-        if (lane == 0 && rank == 0) {
+        // ================= MMA issuer (in pair mode of the leader CTA only): convergent loop, predicated issue =================
+        if (rank == 0) {
+            const uint32_t el = elect_one();
             const uint32_t idesc = umma_idesc2(PAIR ? 2 * BM : BM, BN, 0, B_MN ? 1 : 0);
+            const uint32_t smem_base = smem_u32(smem);
             int s = 0; uint32_t ph = 0;
             uint32_t acc = 0;
             for (int it = 0; it < num_it; ++it) {
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const int ntaps = p.groups[g_begin + it / kchunks].ntaps;
-                const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t a_addr = smem_base + s * STAGE_BYTES;
                 const uint32_t b_addr = a_addr + A_SLOT;
                 for (int t = 0; t < ntaps; ++t) {
-                    const uint64_t adesc = umma_desc(a_addr + t * ROW_BYTES, 16), bdesc = umma_desc(b_addr + t * B_BYTES, B_MN ? 64 * BK * 2 : 16);
+                    const uint32_t a_lo = umma_desc_lo(a_addr + t * ROW_BYTES, 16), b_lo = umma_desc_lo(b_addr + t * B_BYTES, B_MN ? 64 * BK * 2 : 16);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {  // UMMA_K = 16: +32 B along a K-major row, +16 rows (2048 B) of an MN-major tile
-                        if (PAIR) umma_f16_pair(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc, acc);
-                        else umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc, acc);
+                        if (PAIR) umma_f16_pair_p(tmem_base, a_lo + 2 * k, b_lo + (B_MN ? 128 : 2) * k, idesc, acc, el);
+                        else umma_f16_p(tmem_base, a_lo + 2 * k, b_lo + (B_MN ? 128 : 2) * k, idesc, acc, el);
                         acc = 1;
                     }
                 }
-                if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+                if (PAIR) umma_commit_pair_p(&empty_bar[s], el); else umma_commit_p(&empty_bar[s], el);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
-            if (PAIR) umma_commit_pair(&tmem_full_bar); else umma_commit(&tmem_full_bar);
+            if (PAIR) umma_commit_pair_p(&tmem_full_bar, el); else umma_commit_p(&tmem_full_bar, el);
         }
     } else {
         // ================= epilogue: TMEM -> registers -> (+residual, +noise, +bias, lrelu) -> global =================
@@ -227,46 +230,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         __nv_bfloat16* out = p.y + opix * p.Cout + n0;
         const float* res = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
         float* out32 = p.y_f32 ? p.y_f32 + opix * p.Cout + n0 : nullptr;
-        const float slope_gain = p.activate == 1 ? 1.4142135623730951f : 1.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            tmem_wait_ld();
-            if (!valid) continue;
-            if (res) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 rr = reinterpret_cast<const float4*>(res + c0)[i];
-                    r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + rr.x);
-                    r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + rr.y);
-                    r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + rr.z);
-                    r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + rr.w);
-                }
-            }
-            if (out32) {   // fp32 partial result (no epilogue math): consumed as `residual` by the second half
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    reinterpret_cast<float4*>(out32 + c0)[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                                           __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                continue;
-            }
-            uint4 packed[4];
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(packed);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float v0 = __uint_as_float(r[2 * i]) + add, v1 = __uint_as_float(r[2 * i + 1]) + add;
-                if (p.bias) { v0 += p.bias[n0 + c0 + 2 * i]; v1 += p.bias[n0 + c0 + 2 * i + 1]; }
-                if (p.activate) {
-                    v0 = (v0 > 0.f ? v0 : 0.2f * v0) * slope_gain;
-                    v1 = (v1 > 0.f ? v1 : 0.2f * v1) * slope_gain;
-                }
-                h2[i] = __floats2bfloat162_rn(v0, v1);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(out + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = packed[i];
-        }
+        conv_epilogue_row<BN>(tmem_base + ((uint32_t)(q * 32) << 16), valid, p.bias ? p.bias + n0 : nullptr, res, out32, out, add,
+                              p.noise != nullptr && p.noise_w != nullptr, p.activate);
         tc_fence_before();
     }
     __syncthreads();
@@ -445,73 +410,71 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
     if (warp == 0) {
         // ================= producer: the weight once, then pixel boxes across all of this CTA's tiles =================
-        if (lane == 0) {
-            mbar_expect_tx(&w_bar, (uint32_t)(q.n_wtiles * W_TILE));
-            for (int wt = 0; wt < q.kk; ++wt)
+        const uint32_t el = elect_one();
+        const uint32_t w_base = smem_u32(w_smem), a_base = smem_u32(a_ring);
+        mbar_expect_tx_p(&w_bar, (uint32_t)(q.n_wtiles * W_TILE), el);
+        for (int wt = 0; wt < q.kk; ++wt)
+            for (int ck = 0; ck < kchunks; ++ck) {
+                const uint32_t dst = w_base + (uint32_t)((wt * kchunks + ck) * W_TILE);
+                if (B_MN) tma_load_3d_p(dst, &map_w, smem_u32(&w_bar), p.w_cin_offset, wt, ck * BK, el);
+                else tma_load_3d_p(dst, &map_w, smem_u32(&w_bar), p.w_cin_offset + ck * BK, wt, 0, el);
+            }
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
+            const int phase = tile % p.n_phase, rest = tile / p.n_phase;
+            const int img = rest / tiles_img, tile_m = rest - img * tiles_img;
+            const int h0 = (tile_m / tiles_w) * TILE_H, w0 = (tile_m % tiles_w) * TILE_W;
+            for (int g = p.gbegin[phase]; g < p.gbegin[phase + 1]; ++g) {
+                const int x0 = p.in_stride * w0 + p.groups[g].dx, y0 = p.in_stride * h0 + p.groups[g].dy;
                 for (int ck = 0; ck < kchunks; ++ck) {
-                    unsigned char* dst = w_smem + (size_t)(wt * kchunks + ck) * W_TILE;
-                    if (B_MN) tma_load_3d(dst, &map_w, &w_bar, p.w_cin_offset, wt, ck * BK);
-                    else tma_load_3d(dst, &map_w, &w_bar, p.w_cin_offset + ck * BK, wt, 0);
-                }
-            int s = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
-                const int phase = tile % p.n_phase, rest = tile / p.n_phase;
-                const int img = rest / tiles_img, tile_m = rest - img * tiles_img;
-                const int h0 = (tile_m / tiles_w) * TILE_H, w0 = (tile_m % tiles_w) * TILE_W;
-                for (int g = p.gbegin[phase]; g < p.gbegin[phase + 1]; ++g) {
-                    const int x0 = p.in_stride * w0 + p.groups[g].dx, y0 = p.in_stride * h0 + p.groups[g].dy;
-                    for (int ck = 0; ck < kchunks; ++ck) {
-                        mbar_wait(&empty_bar[s], ph ^ 1);
-                        mbar_expect_tx(&full_bar[s], (uint32_t)a_bytes);
-                        tma_load_4d(a_ring + (size_t)s * A_SLOT, &map_x, &full_bar[s], ck * BK, x0, y0, img);
-                        if (++s == STAGES) { s = 0; ph ^= 1; }
-                    }
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx_p(&full_bar[s], (uint32_t)a_bytes, el);
+                    tma_load_4d_p(a_base + (uint32_t)(s * A_SLOT), &map_x, smem_u32(&full_bar[s]), ck * BK, x0, y0, img, el);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc2(BM, BN, 0, B_MN ? 1 : 0);
-            mbar_wait(&w_bar, 0);
+        // ================= MMA issuer: convergent loop, predicated issue =================
+        const uint32_t el = elect_one();
+        const uint32_t idesc = umma_idesc2(BM, BN, 0, B_MN ? 1 : 0);
+        mbar_wait(&w_bar, 0);
+        tc_fence_after();
+        const uint32_t w_addr = smem_u32(w_smem), a_base = smem_u32(a_ring);
+        int s = 0; uint32_t ph = 0;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tl) {
+            const int phase = tile % p.n_phase;
+            const int buf = tl & 1;
+            mbar_wait(&tempty_bar[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));     // the epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t w_addr = smem_u32(w_smem);
-            int s = 0; uint32_t ph = 0;
-            int tl = 0;
-            for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tl) {
-                const int phase = tile % p.n_phase;
-                const int buf = tl & 1;
-                mbar_wait(&tempty_bar[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));     // the epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-                uint32_t acc = 0;
-                for (int g = p.gbegin[phase]; g < p.gbegin[phase + 1]; ++g) {
-                    const TapGroup grp = p.groups[g];
-                    for (int ck = 0; ck < kchunks; ++ck) {
-                        mbar_wait(&full_bar[s], ph);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(a_ring + (size_t)s * A_SLOT);
-                        for (int t = 0; t < grp.ntaps; ++t) {
-                            const uint64_t adesc = umma_desc(a_addr + t * ROW_BYTES, 16);
-                            const uint64_t bdesc = umma_desc(w_addr + (uint32_t)((grp.wt[t] * kchunks + ck) * W_TILE), B_MN ? W_TILE : 16);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+            uint32_t acc = 0;
+            for (int g = p.gbegin[phase]; g < p.gbegin[phase + 1]; ++g) {
+                const TapGroup grp = p.groups[g];
+                for (int ck = 0; ck < kchunks; ++ck) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = a_base + (uint32_t)(s * A_SLOT);
+                    for (int t = 0; t < grp.ntaps; ++t) {
+                        const uint32_t a_lo = umma_desc_lo(a_addr + t * ROW_BYTES, 16);
+                        const uint32_t b_lo = umma_desc_lo(w_addr + (uint32_t)((grp.wt[t] * kchunks + ck) * W_TILE), B_MN ? W_TILE : 16);
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) {
-                                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc, acc);
-                                acc = 1;
-                            }
+                        for (int k = 0; k < BK / 16; ++k) {
+                            umma_f16_p(d_tmem, a_lo + 2 * k, b_lo + (B_MN ? 128 : 2) * k, idesc, acc, el);
+                            acc = 1;
                         }
-                        umma_commit(&empty_bar[s]);
-                        if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
+                    umma_commit_p(&empty_bar[s], el);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull_bar[buf]);
             }
+            umma_commit_p(&tfull_bar[buf], el);
         }
     } else {
         // ================= epilogue warps: drain accumulator (tl & 1) while the next tile's MMAs fill the other =================
         const int qd = warp & 3;
         const int row = qd * 32 + lane;
-        const float slope_gain = p.activate == 1 ? 1.4142135623730951f : 1.f;
         int tl = 0;
         for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tl) {
             const int phase = tile % p.n_phase, rest = tile / p.n_phase;
@@ -529,45 +492,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             __nv_bfloat16* out = p.y + opix * p.Cout;
             const float* res = p.residual ? p.residual + pix * p.Cout : nullptr;
             float* out32 = p.y_f32 ? p.y_f32 + opix * p.Cout : nullptr;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * BN + c0), r);
-                tmem_wait_ld();
-                if (!valid) continue;
-                if (res) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 rr = reinterpret_cast<const float4*>(res + c0)[i];
-                        r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + rr.x);
-                        r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + rr.y);
-                        r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + rr.z);
-                        r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + rr.w);
-                    }
-                }
-                if (out32) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        reinterpret_cast<float4*>(out32 + c0)[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                    continue;
-                }
-                uint4 packed[4];
-                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(packed);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float v0 = __uint_as_float(r[2 * i]) + add, v1 = __uint_as_float(r[2 * i + 1]) + add;
-                    if (p.bias) { v0 += p.bias[c0 + 2 * i]; v1 += p.bias[c0 + 2 * i + 1]; }
-                    if (p.activate) {
-                        v0 = (v0 > 0.f ? v0 : 0.2f * v0) * slope_gain;
-                        v1 = (v1 > 0.f ? v1 : 0.2f * v1) * slope_gain;
-                    }
-                    h2[i] = __floats2bfloat162_rn(v0, v1);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(out + c0);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = packed[i];
-            }
+            conv_epilogue_row<BN>(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * BN), valid, p.bias, res, out32, out, add,
+                                  p.noise != nullptr && p.noise_w != nullptr, p.activate);
             tc_fence_before();                 // this warp's tcgen05.ld of the accumulator are complete (wait::ld above)
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);

@@ -333,7 +333,8 @@ __global__ void __launch_bounds__(256) bias_act_fwd_kernel(const T* __restrict__
     const int cv = C / VN;
     const int64_t total = pixels * cv;
     const float nw = (noise && noise_w) ? noise_w[0] : 0.f;
-    const float gain = activate == 2 ? 1.f : kSqrt2;   // 1: FusedLeakyReLU (x sqrt2), 2: plain LeakyReLU(0.2)
+    const float gain = activate == 1 ? kSqrt2 : 1.f;   // 1: FusedLeakyReLU (x sqrt2), 2: plain LeakyReLU(0.2), 3: ReLU
+    const float neg_slope = activate == 3 ? 0.f : 0.2f;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % cv) * VN;
         const int64_t p = idx / cv;
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(256) bias_act_fwd_kernel(const T* __restrict__
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
             float v = f[i] + add + (bias ? bias[c + i] : 0.f);
-            if (activate) v = (v > 0.f ? v : v * 0.2f) * gain;
+            if (activate) v = (v > 0.f ? v : v * neg_slope) * gain;
             f[i] = v;
         }
         if (VECTOR) { typename VecOf<T>::V v; pack(f, v); *reinterpret_cast<typename VecOf<T>::V*>(y + p * C + c) = v; }
@@ -372,7 +373,8 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const T* __restrict__
 #pragma unroll
     for (int i = 0; i < VN; ++i) bsum[i] = 0.f;
     float nsum = 0.f;
-    const float gain = activate == 2 ? 1.f : kSqrt2;
+    const float gain = activate == 1 ? kSqrt2 : 1.f;
+    const float neg_slope = activate == 3 ? 0.f : 0.2f;
     if (my_lane < lanes) {
         for (int64_t p = p0 + my_lane; p < p1; p += lanes) {
             float g[VN], o[VN];
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const T* __restrict__
             float psum = 0.f;
 #pragma unroll
             for (int i = 0; i < VN; ++i) {
-                if (activate) g[i] *= (o[i] > 0.f ? gain : 0.2f * gain);
+                if (activate) g[i] *= (o[i] > 0.f ? gain : neg_slope * gain);
                 bsum[i] += g[i];
                 psum += g[i];
             }

@@ -194,7 +194,8 @@ class FlatAdam:
     def all_reduce(self, group=None):
         """The ONE collective of the view-sharded step: sum of the flat gradient bucket."""
         import torch.distributed as dist
-        dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
+        with stats.stage("allreduce"):
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
 
     def step(self, grad_scale=1.0, zero_grad=True, graph_safe=True):
         """One Adam step.  Safe to capture in a CUDA graph (step counters, lr and grad_scale live on the device; the

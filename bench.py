@@ -442,13 +442,32 @@ def run_aux_config(args, device):
     return 0
 
 
-def _exit_multi_rank():
-    """Leave without tearing NCCL down: the communicator is referenced by the captured CUDA graph, and
-    barrier()/destroy_process_group() after a graph-captured all-reduce was observed to hang (torch 2.11 / NCCL 2.28).
-    All collectives of the run have completed (device_time_ms ends with a barrier + synchronize)."""
+def _exit_multi_rank(wl=None):
+    """Clean shutdown of a multi-rank run: drop the captured CUDA graph FIRST (it holds the communicator's streams and
+    kernels — destroying the process group underneath a live graph is what hung on torch 2.11 / NCCL 2.28), drain the
+    device, then destroy the process group.  A watchdog turns a teardown that still hangs into a plain exit after 20 s:
+    every collective of the run has completed by then (device_time_ms ends with a barrier + synchronize), the result line is
+    already printed, and the driver must never wait on a wedged rank."""
+    import torch.distributed as dist
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
+
+    def bail():
+        time.sleep(20.0)
+        os._exit(0)
+    threading.Thread(target=bail, daemon=True).start()
+    try:
+        if wl is not None:
+            wl.graph = None
+            wl.static_loss = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+    sys.exit(0)
 
 
 def main():
@@ -528,11 +547,15 @@ def main():
     wl.graph = graph
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
-        _exit_multi_rank()
+        _exit_multi_rank(wl)
 
     if os.environ.get("AGR_STAGE_DETAIL"):   # per-layer-geometry device times of the staged pass (stderr)
         for lab, (t, n) in sorted(st["detail"].items(), key=lambda kv: -kv[1][0]):
             print("%-46s n/step %5.1f  ms/step %8.4f" % (lab, n / args.steps, t / args.steps), file=sys.stderr)
+    # where the step's kernel time sits with respect to the view shard: convolutions of batch-1 tensors (position / other nets,
+    # colour prefix) are REPLICATED on every rank, those of the local view batch are SHARDED (labels carry the batch size)
+    conv_rep = sum(t for lab, (t, n) in st["detail"].items() if " N1 " in lab) / args.steps
+    conv_shard = sum(t for lab, (t, n) in st["detail"].items() if " N1 " not in lab) / args.steps
     ms_step = ms / args.steps
     value = n_views / (ms_step * 1e-3)
     e2e_value = n_views / (ms_e2e / args.steps * 1e-3)
@@ -558,6 +581,11 @@ def main():
                    "library_ops": list(__import__("animatablegaussians_b200.styleunet_ops", fromlist=["x"]).LIBRARY_OPS)},
         "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes},
         "gpu_launches": st["launches"], "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tc, "stage_ms_per_step": stats.stage_ms(st, args.steps),
+        "shard_split_ms_per_step": {"conv_replicated": conv_rep, "conv_sharded": conv_shard,
+                                    "raster_lbs_loss_sharded": sum(stats.stage_ms(st, args.steps).get(k, 0.0) for k in ("raster_fwd", "raster_bwd", "lbs", "loss_head", "avatar_gather")),
+                                    "allreduce": stats.stage_ms(st, args.steps).get("allreduce", 0.0), "adam_replicated": stats.stage_ms(st, args.steps).get("adam", 0.0),
+                                    "grad_bucket_bytes": int(wl.opt.numel) * 4,
+                                    "note": "eager per-call event pairs (rank 0); the act / FIR / weight stages are not split by batch"},
     }
     if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only
         try:
@@ -566,7 +594,7 @@ def main():
             out["cpu_baseline"] = {"value": None, "unit": "views/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
     print(json.dumps(out))
     if world > 1:
-        _exit_multi_rank()
+        _exit_multi_rank(wl)
 
 
 if __name__ == "__main__":

@@ -46,6 +46,11 @@ def copy_python():
                 if os.path.splitext(f)[1] in KEEP_EXT:
                     os.makedirs(os.path.join(PY_DEST, rel), exist_ok=True)
                     shutil.copy2(os.path.join(d, f), os.path.join(PY_DEST, rel, f))
+    # the LPIPS "lin" weights the reference ships next to its code (7 KB of data; `weights` directories are otherwise skipped)
+    lin = os.path.join(B.REF_ROOT, "network", "lpips", "weights", "v0.1", "vgg.pth")
+    if os.path.exists(lin):
+        os.makedirs(os.path.join(PY_DEST, "network", "lpips", "weights", "v0.1"), exist_ok=True)
+        shutil.copy2(lin, os.path.join(PY_DEST, "network", "lpips", "weights", "v0.1", "vgg.pth"))
     pkg = os.path.join(EXT_DEST, "diff_gaussian_rasterization_depth_alpha")
     os.makedirs(pkg, exist_ok=True)
     shutil.copy2(os.path.join(B.RAST, "diff_gaussian_rasterization_depth_alpha", "__init__.py"), os.path.join(pkg, "__init__.py"))

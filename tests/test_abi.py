@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 
 def test_python_binding_covers_every_declared_symbol(built_lib):
-    from animatablegaussians_b200 import _lib, avatar, lbs, loss, optim, rasterizer, smpl_lbs, styleunet_ops  # noqa: F401  (registering modules)
+    from animatablegaussians_b200 import _lib, avatar, lbs, loss, lpips, optim, rasterizer, smpl_lbs, styleunet_ops  # noqa: F401  (registering modules)
     _lib.load()
     assert set(declared_symbols()) <= set(_lib.SYMBOLS), set(declared_symbols()) - set(_lib.SYMBOLS)
 

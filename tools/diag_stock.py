@@ -39,7 +39,11 @@ def main():
         a = T._run("reference", "avatar", inp, os.path.join(tmp, "a.npz"), state)
         a2 = T._run("reference", "avatar", inp, os.path.join(tmp, "a2.npz"), state)
         b = T._run("dropin", "avatar", inp, os.path.join(tmp, "b.npz"), state)
-        print("==== upstream gradient:", mode, "img", img, "mask coverage %.3f" % float((a["mask_map"] > 0.5).mean()))
+        print("==== upstream gradient:", mode, "img", img, "mask coverage %.3f" % float((a["mask_map"] > 0.5).mean()), "mask mean %.3f" % float(a["mask_map"].mean()))
+        for k in ("pg:positions", "pg:scales", "pg:opacity", "scaling", "offset"):
+            v = a[k].astype(np.float64)
+            print("   %-14s shape %s  min %s  max %s  mean %.4g  std %.4g" % (k, v.shape, np.round(v.min(0), 4) if v.ndim == 2 and v.shape[1] <= 4 else round(float(v.min()), 4),
+                  np.round(v.max(0), 4) if v.ndim == 2 and v.shape[1] <= 4 else round(float(v.max()), 4), v.mean(), v.std()))
         for k in sorted(a.files):
             if not (k.startswith("dpg:") or k.startswith("grad:")):
                 continue
