@@ -24,7 +24,7 @@ import contextlib
 import ctypes as C
 import os
 
-from . import _lib, camera, lbs, stats
+from . import _lib, camera, lbs, parallel, stats
 from . import styleunet_ops as ops
 from .rasterizer import GaussianRasterizer, rasterize_gaussians_batched
 from .styleunet import DualStyleUNet
@@ -160,6 +160,9 @@ class AvatarNet(nn.Module):
         self.random_style = opt.get('random_style', False)
         self.with_viewdirs = opt.get('with_viewdirs', True)
         self.concurrent_nets = os.environ.get('AGR_SERIAL_NETS', '0') != '1'   # render_views: nets on parallel streams
+        # render_views under torch.distributed: each view-independent network runs on ONE owner rank (parallel.py)
+        self.net_parallel = os.environ.get('AGR_NET_PARALLEL', '1') != '0'
+        self._np_meta, self._np_dummy = {}, None
         if device is None:
             try:
                 import config  # the reference's global config module, when running under main_avatar.py
@@ -424,18 +427,8 @@ class AvatarNet(nn.Module):
         # cam_pos = -inv(R) t  == camera centre == campos of the raster settings
         return {"settings": bs, "cam_pos": bs.campos, "V": len(extrs)}
 
-    def render_views(self, items, extrs=None, intrs=None, img_w=None, img_h=None, bg_color=(0., 0., 0.), return_depth=False,
-                     views=None):
-        """items: pose-level entries ('smpl_pos_map', 'cano2live_jnt_mats'); extrs/intrs: V host (numpy) camera
-        matrices, or `views` = prepare_views(...).  Returns rgb_maps (V,H,W,3), mask_maps (V,H,W,1)
-        [, depth_maps (V,H,W,1)], offset, pos_map — per view identical to render() with that camera."""
-        if views is None:
-            views = self.prepare_views(extrs, intrs, img_w, img_h, bg_color)
-        V = views["V"]
-        pose_map = items['smpl_pos_map'][:3]
-        # The three U-Nets are independent until the rasterizer.  Position and "other" nets (batch 1: 2 - 128 CTAs per
-        # convolution, less than the 148 SMs) run on two side streams next to the colour net, forward AND backward
-        # (autograd replays each node on its forward stream); inside a captured step they become parallel graph branches.
+    def _replicated_nets(self, items, pose_map, views, V):
+        """Every rank (or the only one) runs the three networks -> (position attributes (N,3), other attributes (N,8), colours)."""
         main = torch.cuda.current_stream()
         side = self._side_streams() if (self.concurrent_nets and pose_map.is_cuda) else None
         if side is not None:
@@ -447,7 +440,6 @@ class AvatarNet(nn.Module):
         with torch.cuda.stream(side[1]) if side is not None else contextlib.nullcontext():
             of, ob = self.other_net.forward_maps([self.other_style], pose_map[None])
             ogather = self._gather_pair(of, ob)
-        pos_map = None   # (the (S,2S,3) map view is only produced by render(); the trainer reads it for visualisation)
         if self.with_viewdirs:
             with torch.no_grad():
                 live = lbs.skin_points(self.lbs, items['cano2live_jnt_mats'], self.init_points, self.cano_nmls)
@@ -464,6 +456,87 @@ class AvatarNet(nn.Module):
             for st, t in zip(side, (pgather, ogather)):
                 main.wait_stream(st)
                 t.record_stream(main)
+        return pgather, ogather, colors
+
+    def _owner_computes(self, items, pose_map, views, V):
+        """Same three results with each view-independent network on ONE owner rank (animatablegaussians_b200/parallel.py):
+        position net on rank 0, "other" net on rank 1, colour prefix on rank 2 (mod world size); owners broadcast what the
+        rendering ranks need, the backward pass reduces the ranks' gradients onto the owner.  The view-dependent colour tail
+        and the view-direction net run on every rank for its own views."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        own_p, own_o, own_c = 0, 1 % world, 2 % world
+        if self._np_dummy is None:
+            self._np_dummy = torch.zeros(1, device=pose_map.device, requires_grad=True)
+
+        def exchange(key, owner, tensors):
+            if key not in self._np_meta:          # first (eager) call: the receivers learn shapes and dtype
+                self._np_meta[key] = parallel.share_meta(owner, tensors)
+            metas, dtype = self._np_meta[key]
+            return parallel.owner_broadcast(owner, metas, dtype, self._np_dummy, tensors)
+
+        # networks this rank owns run next to each other: position / other nets on the side streams, the colour net on the
+        # main stream (as in the replicated scheme); the exchanges follow in one fixed order on the main stream
+        main = torch.cuda.current_stream()
+        side = self._side_streams() if self.concurrent_nets else None
+        pt, ot = [], []
+        if rank == own_p:
+            if side is not None:
+                side[0].wait_stream(main)
+            with torch.cuda.stream(side[0]) if side is not None else contextlib.nullcontext():
+                pt = [self._gather_pair(*self.position_net.forward_maps([self.position_style], pose_map[None]))]
+        if rank == own_o:
+            if side is not None:
+                side[1].wait_stream(main)
+            with torch.cuda.stream(side[1]) if side is not None else contextlib.nullcontext():
+                ot = [self._gather_pair(*self.other_net.forward_maps([self.other_style], pose_map[None]))]
+        prefix, ct = None, []
+        if self.with_viewdirs:
+            with torch.no_grad():
+                live = lbs.skin_points(self.lbs, items['cano2live_jnt_mats'], self.init_points, self.cano_nmls)
+            if rank == own_c:
+                prefix = self.color_net.forward_prefix([self._color_style()], pose_map[None])
+                ct = self.color_net.tail_state(prefix)
+            else:
+                prefix = self.color_net.tail_prefix([self._color_style()])
+        elif rank == own_c:
+            ct = [self._gather_pair(*self.color_net.forward_maps([self._color_style()], pose_map[None]))]
+        if side is not None:
+            for st, ts in ((side[0], pt), (side[1], ot)):
+                if ts:
+                    main.wait_stream(st)
+                    ts[0].record_stream(main)
+        (pgather,) = exchange("position", own_p, pt)
+        (ogather,) = exchange("other", own_o, ot)
+        if not self.with_viewdirs:
+            (colors,) = exchange("color", own_c, ct)
+            return pgather, ogather, colors
+        state = exchange("color_prefix", own_c, ct)
+        prefix = self.color_net.with_tail_state(prefix, list(state))
+        fv, bv = self.get_viewdir_feat_batched(live, views["cam_pos"])
+        cf, cb = self.color_net.forward_view_tail(prefix, fv, bv, as_pair=True)
+        colors = self._gather_pair(cf, cb)
+        if V == 1:
+            colors = colors[None]
+        return pgather, ogather, colors
+
+    def render_views(self, items, extrs=None, intrs=None, img_w=None, img_h=None, bg_color=(0., 0., 0.), return_depth=False,
+                     views=None):
+        """items: pose-level entries ('smpl_pos_map', 'cano2live_jnt_mats'); extrs/intrs: V host (numpy) camera
+        matrices, or `views` = prepare_views(...).  Returns rgb_maps (V,H,W,3), mask_maps (V,H,W,1)
+        [, depth_maps (V,H,W,1)], offset, pos_map — per view identical to render() with that camera."""
+        if views is None:
+            views = self.prepare_views(extrs, intrs, img_w, img_h, bg_color)
+        V = views["V"]
+        pose_map = items['smpl_pos_map'][:3]
+        # The three U-Nets are independent until the rasterizer.  Position and "other" nets (batch 1: 2 - 128 CTAs per
+        # convolution, less than the 148 SMs) run on two side streams next to the colour net, forward AND backward
+        # (autograd replays each node on its forward stream); inside a captured step they become parallel graph branches.
+        if self.net_parallel and pose_map.is_cuda and parallel.active():
+            pgather, ogather, colors = self._owner_computes(items, pose_map, views, V)
+        else:
+            pgather, ogather, colors = self._replicated_nets(items, pose_map, views, V)
+        pos_map = None   # (the (S,2S,3) map view is only produced by render(); the trainer reads it for visualisation)
         cano_pts = 0.05 * pgather + self.cano_gaussian_model.get_xyz
         opacity, scales, rotations = self._activate_others(ogather)
         nonrigid_offset = cano_pts - self.init_points

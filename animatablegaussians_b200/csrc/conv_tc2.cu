@@ -543,16 +543,17 @@ int conv_tc_generation() {
     return g_generation;
 }
 
-// The persistent 64-channel kernel is OFF unless AGR_CONV_PERSISTENT=1: on B200 it measured the same as one tile per CTA on
-// the 16 x 512^2 64 -> 64 layer (0.81 vs 0.81 ms) and slower on the transposed 128 -> 64 layer (0.86 vs 0.73 ms) —
-// profiles/r02_conv_generations.txt; the layer is not bound by what this kernel removes.
+// The persistent 64-channel kernel (AGR_CONV_PERSISTENT=0 switches it off) is used for single-phase geometries only: with the
+// warp-uniform issue loop it measured 0.55 vs 0.60 ms on the 16 x 512^2 64 -> 64 layer, but 0.62 vs 0.52 ms on the transposed
+// 128 -> 64 layer, whose four output phases have 1-4 taps each (profiles/r02_conv_generations_b.txt).
 static int g_persistent = -1;
 
 // Persistent kernel: Cout = 64, the whole weight fits next to a >= 3-deep box ring, and there are several waves of tiles.
 static bool use_v3(const AgrConvGeom& g) {
-    if (g_persistent < 0) { const char* e = getenv("AGR_CONV_PERSISTENT"); g_persistent = e ? atoi(e) : 0; }
+    if (g_persistent < 0) { const char* e = getenv("AGR_CONV_PERSISTENT"); g_persistent = e ? atoi(e) : 1; }
     if (!g_persistent || conv_tc_generation() != 0) return false;
     if (g.Cout != 64 || g.Cin % 64 || g.Cin > 128) return false;
+    if (g.transposed && g.stride > 1) return false;      // several output phases: see above
     const int s = g.transposed ? g.stride : 1;
     const long tiles = (long)g.N * (((g.OH + s - 1) / s + v2::TILE_H - 1) / v2::TILE_H) * (((g.OW + s - 1) / s + v2::TILE_W - 1) / v2::TILE_W) * s * s;
     return tiles >= 4 * 148 && g.ksize * g.ksize * (g.Cin / 64) * v3::W_TILE + 3 * v2::A_SLOT + 1024 <= v2::MAX_SMEM;

@@ -64,6 +64,9 @@ class FlatAdam:
         self._seg_step = torch.zeros(S, dtype=torch.int32, device=dev)
         self._seg_corr = torch.zeros(S, 2, dtype=torch.float32, device=dev)
         pin = dev.type == "cuda"
+        # True: parameters without a gradient on THIS rank still step — for the owner-computes multi-GPU scheme
+        # (parallel.py), where the all-reduce delivers the owner's gradient into the (locally zero) bucket segment
+        self.assume_all_active = False
         self._h_active = torch.ones(S, dtype=torch.int32).pin_memory() if pin else torch.ones(S, dtype=torch.int32)
         self._seg_active = torch.ones(S, dtype=torch.int32, device=dev)
         self._h_hyper = torch.tensor([lr, 1.0], dtype=torch.float32)
@@ -168,7 +171,7 @@ class FlatAdam:
         views, grads, act = [], [], []
         for p, v in zip(self.params, self._grad_views):
             g = p.grad
-            act.append(0 if g is None else 1)
+            act.append(0 if (g is None and not self.assume_all_active) else 1)
             if g is None or g.data_ptr() == v.data_ptr():
                 continue
             views.append(v)

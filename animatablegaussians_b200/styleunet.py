@@ -294,6 +294,11 @@ class DualStyleUNet(nn.Module):
         self.iwt = InverseHaarTransform(out_ch)
         self.n_latent = self.log_size * 2 - (self.middle_log_size * 2 - 1) + 1
         self.view_level = 8  # loop index after which the view feature is added (dual_styleunet.py:881,900)
+        # the two decoders share the encoder output and nothing else: the second one runs on a side stream, forward AND
+        # backward (autograd replays each node on its forward stream) — their batch-1 layers launch 2 - 128 CTAs each
+        import os
+        self.concurrent_decoders = os.environ.get("AGR_SERIAL_DECODERS", "0") != "1"
+        self._side = None
 
     # ------------------------------------------------------------------ pieces
     def make_noise(self, device, zero_noise=False):
@@ -355,27 +360,51 @@ class DualStyleUNet(nn.Module):
             return out, skip
         return self.iwt(skip)
 
-    def weight_plan(self, latent):
+    def _both_decoders(self, run1, run2, ref):
+        """(run1(), run2()) with run2 on this net's side stream when `ref` lives on a GPU."""
+        if not (self.concurrent_decoders and ref.is_cuda):
+            return run1(), run2()
+        if self._side is None or self._side.device != ref.device:
+            self._side = torch.cuda.Stream(ref.device)
+        main = torch.cuda.current_stream(ref.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            r2 = run2()
+        r1 = run1()
+        main.wait_stream(self._side)
+        for t in (r2 if isinstance(r2, (tuple, list)) else (r2,)):
+            if isinstance(t, torch.Tensor):
+                t.record_stream(main)
+        return r1, r2
+
+    def weight_plan(self, latent, tail_only=False):
         """Conv-ready operands of EVERY layer for this latent, prepared by the grouped kernels (a few launches instead
         of one per layer): encoder / combiner equalised convs (scale only) and the two decoders' modulated convs
-        (style modulation of latent[:, i] as _decode indexes it).  Only for the single-style case the avatar runs."""
+        (style modulation of latent[:, i] as _decode indexes it).  Only for the single-style case the avatar runs.
+        `tail_only`: just the layers forward_view_tail() runs (a rank that receives the prefix state from its owner)."""
         if latent.shape[0] != 1 or not latent.is_cuda:
             return None
         entries = []
+        first = (self.view_level + 2) // 2 if tail_only else 0      # first decoder level of the plan
 
         def plain(layer):   # ConvLayer: [Blur,] EqualConv2d [, FusedLeakyReLU]
             conv = layer[1] if layer.has_blur else layer[0]
             entries.append((conv.weight, None, conv.scale, False))
 
-        plain(self.conv_in)
-        for from_rgb, cond_conv in zip(self.from_rgbs, self.cond_convs):
-            plain(from_rgb.conv); plain(cond_conv.conv1); plain(cond_conv.conv2)
-        for comb in self.comb_convs:
-            plain(comb)
+        if not tail_only:
+            plain(self.conv_in)
+            for from_rgb, cond_conv in zip(self.from_rgbs, self.cond_convs):
+                plain(from_rgb.conv); plain(cond_conv.conv1); plain(cond_conv.conv2)
+            for comb in self.comb_convs:
+                plain(comb)
+        else:
+            for lvl in range(first, len(self.to_rgbs1)):
+                if 0 < 2 * lvl < 2 * len(self.comb_convs):
+                    plain(self.comb_convs[-1 - lvl])
         mods = []   # (ModulatedConv2d, latent index) in _decode's order
         for convs, rgbs in ((self.convs1, self.to_rgbs1), (self.convs2, self.to_rgbs2)):
-            mods += [(sc.conv, i) for i, sc in enumerate(convs)]
-            mods += [(rgb.conv, 2 * lvl + 2) for lvl, rgb in enumerate(rgbs)]
+            mods += [(sc.conv, i) for i, sc in enumerate(convs) if i >= 2 * first]
+            mods += [(rgb.conv, 2 * lvl + 2) for lvl, rgb in enumerate(rgbs) if lvl >= first]
         if latent.dtype == torch.float32 and latent.dim() == 3:
             styles = ops.equal_linear_group(latent, [(c.modulation, i) for c, i in mods])
         else:
@@ -407,8 +436,8 @@ class DualStyleUNet(nn.Module):
         noise = [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
         with ops.weight_plan(self.weight_plan(latent)):
             cond_list = self.encode(ops.to_compute(condition_img))
-            return (self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, view_feature1),
-                    self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, view_feature2))
+            return self._both_decoders(lambda: self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, view_feature1),
+                                       lambda: self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, view_feature2), cond_list[0])
 
     # ------------------------------------------------------------------ view-batch split (exact)
     def forward_prefix(self, styles, condition_img):
@@ -420,9 +449,34 @@ class DualStyleUNet(nn.Module):
         with ops.weight_plan(plan):
             cond_list = self.encode(ops.to_compute(condition_img))
             stop = self.view_level + 2
-            s1 = self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, None, stop=stop)
-            s2 = self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, None, stop=stop)
+            s1, s2 = self._both_decoders(lambda: self._decode(self.convs1, self.to_rgbs1, cond_list, latent, noise, None, stop=stop),
+                                         lambda: self._decode(self.convs2, self.to_rgbs2, cond_list, latent, noise, None, stop=stop), cond_list[0])
         return dict(latent=latent, noise=noise, cond_list=cond_list, s1=s1, s2=s2, plan=plan)
+
+    # ---- prefix state exchange (animatablegaussians_b200/parallel.py: the prefix runs on one owner rank) -----------------------
+    def _tail_cond_index(self):
+        """(Negative) indices into cond_list that the tail reads: `cond_list[-1 - lvl]` of each tail level (see _decode)."""
+        first = (self.view_level + 2) // 2
+        return [-1 - lvl for lvl in range(first, len(self.to_rgbs1)) if 0 < 2 * lvl < 2 * len(self.comb_convs)]
+
+    def tail_state(self, prefix):
+        """The tensors forward_view_tail() reads from a prefix: both decoders' (out, skip) + the skip features of the tail levels."""
+        return [prefix["s1"][0], prefix["s1"][1], prefix["s2"][0], prefix["s2"][1]] + [prefix["cond_list"][k] for k in self._tail_cond_index()]
+
+    def with_tail_state(self, prefix, tensors):
+        """`prefix` (from forward_prefix or tail_prefix) with the exchanged tensors in place of its own."""
+        cond = list(prefix["cond_list"])
+        for k, t in zip(self._tail_cond_index(), tensors[4:]):
+            cond[k] = t
+        return dict(prefix, s1=(tensors[0], tensors[1]), s2=(tensors[2], tensors[3]), cond_list=cond)
+
+    def tail_prefix(self, styles):
+        """What a rank that does NOT run the prefix needs before forward_view_tail(): latent, noise buffers, the tail layers'
+        conv operands; the state tensors come from the owner (with_tail_state)."""
+        latent = self._latent(styles, False, 1, None, None)
+        noise = [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
+        return dict(latent=latent, noise=noise, cond_list=[None] * (1 + len(self.from_rgbs)), s1=None, s2=None,
+                    plan=self.weight_plan(latent, tail_only=True))
 
     def forward_view_tail(self, prefix, view_feature1, view_feature2, as_pair=False):
         """View-dependent remainder for a BATCH of V views (view features (V,128,h,w)): add the (bilinearly resized)

@@ -95,6 +95,8 @@ class ProductWorkload:
         # random-init nets away from the emulated pre-trained state within a few steps (Gaussians grow until they fill
         # the screen), so the workload would not be stationary.  The Adam arithmetic does not depend on lr.
         self.opt = optim.FlatAdam(self.net.parameters(), lr=lr)
+        # owner-computes (parallel.py): a rank holds no gradient for the networks it does not run; the all-reduce brings it
+        self.opt.assume_all_active = world > 1 and self.net.net_parallel
         extrs, Ks = S.ring_cameras(n_views, img=IMG)
         self.views = list(range(rank, n_views, world))
         self.extrs, self.Ks = [extrs[v] for v in self.views], [Ks[v] for v in self.views]
@@ -324,6 +326,41 @@ def run_check(args, rank, world, device):
     return 0 if (rank != 0 or not args.check_against or res["vs_n1"]["ok"]) else 1
 
 
+def run_precision_check(args, device):
+    """--check-bf16: the benched configuration (bf16 StyleUNet, 512 -> 1024 maps, 16 views, 300k Gaussians) against the same step
+    in fp32 (the parity mode, pinned to the reference by tests/) from the same seeded state: relative L2 of the loss, the
+    rendered maps and the gradient bucket per network.  One eager step each, eval mode (no view-direction noise)."""
+    from animatablegaussians_b200 import styleunet_ops as ops
+    res, keep = {}, {}
+    for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        wl = ProductWorkload(0, 1, device, lr=1e-3, dtype=dt)
+        wl.net.eval()
+        with ops.step_arena():
+            items = {"smpl_pos_map": wl.d_pose, "cano2live_jnt_mats": wl.d_mats}
+            out = wl.net.render_views(items, return_depth=True, views=wl.views_dev)
+            loss = wl._loss(out)
+            loss.backward()
+        wl.opt.gather_grads()
+        torch.cuda.synchronize()
+        segs = {}
+        for pname, p in wl.net.named_parameters():
+            if p.requires_grad and p.grad is not None:
+                segs.setdefault(pname.split(".")[0], []).append(p.grad.detach().flatten().float())
+        keep[name] = {"loss": float(loss), "rgb": out["rgb_maps"].detach().float().cpu(), "mask": out["mask_maps"].detach().float().cpu(),
+                      "depth": out["depth_maps"].detach().float().cpu(), "grads": {k: torch.cat(v).cpu() for k, v in segs.items()}}
+        del wl, out, loss
+        torch.cuda.empty_cache()
+    ops.set_compute_dtype(torch.float32)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    a, b = keep["bf16"], keep["fp32"]
+    res = {"loss_fp32": b["loss"], "loss_bf16": a["loss"], "loss_rel": abs(a["loss"] - b["loss"]) / abs(b["loss"]),
+           "rgb_rel_l2": rel(a["rgb"], b["rgb"]), "mask_rel_l2": rel(a["mask"], b["mask"]), "depth_rel_l2": rel(a["depth"], b["depth"]),
+           "grad_rel_l2": {k: rel(a["grads"][k], b["grads"][k]) for k in b["grads"] if k in a["grads"]},
+           "config": "BASELINE configs[3]: 300k Gaussians, 16 views @1024^2, maps 1024^2; bf16 StyleUNet vs fp32 StyleUNet, same state"}
+    print(json.dumps({"check_bf16": res}))
+    return 0
+
+
 def _time_ms(fn, steps, warmup):
     for _ in range(max(warmup, 3)):
         fn()
@@ -484,6 +521,7 @@ def main():
                     help="StyleUNet compute dtype of the product arm: bf16 (tcgen05, the headline) or fp32 (CUDA-core parity kernels) — the "
                          "fp32 line separates the view-batch restructuring from the precision / tensor-core share of the speed-up")
     ap.add_argument("--check", action="store_true", help="one eager step: loss / gradient / parameter-delta checksums (see run_check)")
+    ap.add_argument("--check-bf16", action="store_true", help="one eager step in bf16 and in fp32 from the same state: relative L2 of loss / maps / gradients (see run_precision_check)")
     ap.add_argument("--check-against", default=None, help="gpurun_out/check_n1.pt of the 1-GPU --check run to compare with")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -505,6 +543,8 @@ def main():
 
     if args.check:
         sys.exit(run_check(args, rank, world, device))
+    if args.check_bf16:
+        sys.exit(run_precision_check(args, device))
     if args.config in (1, 2, 3):
         if rank == 0:
             run_aux_config(args, device)
@@ -575,7 +615,7 @@ def main():
                                "depth term, offset regulariser), synthetic %dk-Gaussian capsule avatar, 1 pose x %d views @1024x1024, "
                                "%s StyleUNet, view-sharded over %d GPU(s)" % (args.config - 1, wl.P // 1000, n_views, args.dtype, world),
                    "gaussians": wl.P, "views_per_step": n_views, "views_per_rank": len(wl.views), "image": [IMG, IMG],
-                   "parallelism": "view-shard x%d + 1 all-reduce" % world, "cuda_graph": not args.no_graph,
+                   "parallelism": ("view-shard x%d + 1 all-reduce" % world) + (", per-pose networks on owner ranks (broadcast / reduce of their outputs)" if (world > 1 and wl.net.net_parallel) else ""), "cuda_graph": not args.no_graph,
                    "tile_instances_per_step": instances,
                    "l2": "step working set (activations, maps, instance streams: several GB) exceeds the 126 MB L2; no explicit flush",
                    "library_ops": list(__import__("animatablegaussians_b200.styleunet_ops", fromlist=["x"]).LIBRARY_OPS)},

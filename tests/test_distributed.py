@@ -90,3 +90,42 @@ def test_lazy_gradient_gather_semantics():
         r.grad = None
     f(ref, x2).backward()
     assert torch.allclose(flat(opt.flat_grad), torch.cat([r.grad.reshape(-1) for r in ref]), rtol=1e-6, atol=1e-7)
+
+
+def _owner_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from animatablegaussians_b200 import parallel
+    owner = 1
+    torch.manual_seed(3)
+    w = torch.randn(5, 3, requires_grad=True)                         # the owner's "network"
+    x4 = torch.randn(1, 4, 3, 2).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    dummy = torch.zeros(1, requires_grad=True)
+    tensors = [w * 2.0, x4 * 1.0] if rank == owner else []
+    metas, dtype = parallel.share_meta(owner, tensors)
+    a, b = parallel.owner_broadcast(owner, metas, dtype, dummy, tensors)
+    # every rank uses the outputs with its own (rank-dependent) weights, like each rank rendering its own views
+    loss = (a * (rank + 1.0)).sum() + (b * b * (rank + 2.0)).sum()
+    loss.backward()
+    ret[rank] = (a.detach().clone(), b.detach().clone(), b.is_contiguous(memory_format=torch.channels_last),
+                 None if w.grad is None else w.grad.clone(), None if x4.grad is None else x4.grad.clone())
+    dist.destroy_process_group()
+
+
+def test_owner_computes_broadcast_and_reduce():
+    """parallel.owner_broadcast (gloo, world_size 2): every rank sees the owner's tensors (channels_last preserved); the
+    owner's inputs receive the SUM of the ranks' gradients, the other ranks' copies of the network receive nothing."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_owner_worker, args=(world, port, ret), nprocs=world, join=True)
+    a0, b0, cl0, gw0, gx0 = ret[0]
+    a1, b1, cl1, gw1, gx1 = ret[1]
+    torch.manual_seed(3)
+    w = torch.randn(5, 3)
+    x4 = torch.randn(1, 4, 3, 2)
+    assert torch.equal(a0, a1) and torch.equal(a0, w * 2.0) and torch.equal(b0, b1) and torch.equal(b0, x4) and cl0 and cl1
+    assert gw0 is None and gx0 is None                                          # rank 0 does not own the network
+    assert torch.allclose(gw1, torch.full((5, 3), 2.0 * (1.0 + 2.0)))            # d/dw of sum_r (2w)(r+1)
+    assert torch.allclose(gx1, 2.0 * x4 * (2.0 + 3.0))                            # d/dx of sum_r x^2 (r+2)
