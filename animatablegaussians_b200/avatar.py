@@ -161,7 +161,9 @@ class AvatarNet(nn.Module):
         self.with_viewdirs = opt.get('with_viewdirs', True)
         self.concurrent_nets = os.environ.get('AGR_SERIAL_NETS', '0') != '1'   # render_views: nets on parallel streams
         # render_views under torch.distributed: each view-independent network runs on ONE owner rank (parallel.py)
-        self.net_parallel = os.environ.get('AGR_NET_PARALLEL', '1') != '0'
+        # AGR_NET_PARALLEL: 0 = never, 1 = whenever world_size > 1, unset = from 3 ranks on (at 2 ranks one of them would own
+        # two of the three networks: measured 34.3 ms against 30.5 ms for the replicated scheme, profiles/SUMMARY_r02.md)
+        self.net_parallel_min_world = {'0': 1 << 30, '1': 2}.get(os.environ.get('AGR_NET_PARALLEL', ''), 3)
         self._np_meta, self._np_dummy = {}, None
         if device is None:
             try:
@@ -427,6 +429,14 @@ class AvatarNet(nn.Module):
         # cam_pos = -inv(R) t  == camera centre == campos of the raster settings
         return {"settings": bs, "cam_pos": bs.campos, "V": len(extrs)}
 
+    @property
+    def net_parallel(self):
+        """True when render_views() runs the per-pose networks owner-computes style under the current process group."""
+        if not parallel.active():
+            return False
+        import torch.distributed as dist
+        return dist.get_world_size() >= self.net_parallel_min_world
+
     def _replicated_nets(self, items, pose_map, views, V):
         """Every rank (or the only one) runs the three networks -> (position attributes (N,3), other attributes (N,8), colours)."""
         main = torch.cuda.current_stream()
@@ -532,7 +542,7 @@ class AvatarNet(nn.Module):
         # The three U-Nets are independent until the rasterizer.  Position and "other" nets (batch 1: 2 - 128 CTAs per
         # convolution, less than the 148 SMs) run on two side streams next to the colour net, forward AND backward
         # (autograd replays each node on its forward stream); inside a captured step they become parallel graph branches.
-        if self.net_parallel and pose_map.is_cuda and parallel.active():
+        if pose_map.is_cuda and self.net_parallel:
             pgather, ogather, colors = self._owner_computes(items, pose_map, views, V)
         else:
             pgather, ogather, colors = self._replicated_nets(items, pose_map, views, V)

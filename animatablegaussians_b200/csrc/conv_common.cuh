@@ -88,6 +88,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra TCW_%=;\n\t"
         "TCD_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Wait of a whole warp on one barrier phase, in LOCKSTEP: every lane polls, the warp leaves together once all lanes have seen
+// the phase complete (a warp vote per iteration).  32 lanes polling the same parity INDEPENDENTLY is not safe for barriers
+// that go through many phases: a lane that falls a full ring cycle behind its siblings sees the parity it waits for come
+// round again and can be left waiting when the kernel ends — the intermittent hang of the first warp-uniform version
+// (profiles/r02_hang_hunt.txt).  The vote also keeps the loop exit warp-uniform, so ptxas keeps the code behind it on the
+// uniform datapath (a `lane == 0` poll + __syncwarp() made it fall back to vector registers + R2UR per MMA operand).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!__all_sync(0xffffffffu, ok));
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -215,6 +229,11 @@ __device__ __forceinline__ void tma_load_3d_pair_p(uint32_t dst, const CUtensorM
 // ---- epilogue of the forward-form kernels: one accumulator row (TMEM lane) per thread, BN columns in chunks of 32 ----------
 //   y = act(acc + residual + noise + bias) -> bf16, or the raw fp32 accumulator (out32).  Launches without any of that (every
 //   data gradient) take the `plain` path: tcgen05.ld, 16 packs, 4 x 16-byte stores per chunk.
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_row(uint32_t taddr, bool valid, const float* __restrict__ bias, const float* __restrict__ res,
                                                   float* __restrict__ out32, __nv_bfloat16* __restrict__ out, float add, bool has_noise, int activate) {
@@ -244,9 +263,9 @@ __device__ __forceinline__ void conv_epilogue_row(uint32_t taddr, bool valid, co
             }
             if (out32) {   // fp32 partial result (no epilogue math): consumed as `residual` by the second half of a split contraction
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    reinterpret_cast<float4*>(out32 + c0)[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                                           __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                for (int i = 0; i < 4; ++i)
+                    st_global_256(out32 + c0 + 8 * i, make_uint4(r[8 * i], r[8 * i + 1], r[8 * i + 2], r[8 * i + 3]),
+                                  make_uint4(r[8 * i + 4], r[8 * i + 5], r[8 * i + 6], r[8 * i + 7]));
                 continue;
             }
 #pragma unroll
@@ -266,9 +285,9 @@ __device__ __forceinline__ void conv_epilogue_row(uint32_t taddr, bool valid, co
                 h2[2 * i + 1] = __floats2bfloat162_rn(v2, v3);
             }
         }
-        uint4* dst = reinterpret_cast<uint4*>(out + c0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = packed[i];
+        // two 256-bit stores (STG.256: whole 32-byte sectors) instead of four 128-bit ones
+        st_global_256(out + c0, packed[0], packed[1]);
+        st_global_256(out + c0 + 16, packed[2], packed[3]);
     }
 }
 

@@ -97,7 +97,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int it = 0; it < num_kb; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_wait_warp(&empty_bar[s], ph ^ 1);
             const int tap = t_begin + it / kchunks, ck = it % kchunks;
             const uint32_t a_dst = smem_base + s * STAGE_BYTES;
             const uint32_t b_dst = a_dst + A_BYTES;
@@ -121,7 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int it = 0; it < num_kb; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&full_bar[s], ph);
+            mbar_wait_warp(&full_bar[s], ph);
             tc_fence_after();
             const uint32_t a_lo = umma_desc_lo(smem_base + s * STAGE_BYTES, 16);
             const uint32_t b_lo = umma_desc_lo(smem_base + s * STAGE_BYTES + A_BYTES, B_MN ? 64 * BK * 2 : 16);
@@ -226,7 +226,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int ydx = p.x_shifted ? 0 : grp.dx, ydy = p.x_shifted ? 0 : grp.dy;
         int s = 0; uint32_t ph = 0;
         for (int it = 0; it < num_kb; ++it) {
-            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_wait_warp(&empty_bar[s], ph ^ 1);
             const int b = box0 + it;
             const int img = b / boxes_img, t = b - img * boxes_img;
             const int h0 = (t / tiles_w) * TILE_H, w0 = (t % tiles_w) * TILE_W;
@@ -247,7 +247,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         int s = 0; uint32_t ph = 0;
         uint32_t acc = 0;
         for (int it = 0; it < num_kb; ++it) {
-            mbar_wait(&full_bar[s], ph);
+            mbar_wait_warp(&full_bar[s], ph);
             tc_fence_after();
             const uint32_t a_addr = smem_base + s * stage_bytes;
             const uint32_t b_addr = a_addr + a_bytes;

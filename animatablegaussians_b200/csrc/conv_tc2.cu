@@ -151,7 +151,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const uint32_t smem_base = smem_u32(smem);
         int s = 0; uint32_t ph = 0;
         for (int it = 0; it < num_it; ++it) {
-            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_wait_warp(&empty_bar[s], ph ^ 1);
             const TapGroup grp = p.groups[g_begin + it / kchunks];
             const int ck = it % kchunks;
             const uint32_t a_dst = smem_base + s * STAGE_BYTES;
@@ -196,7 +196,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             int s = 0; uint32_t ph = 0;
             uint32_t acc = 0;
             for (int it = 0; it < num_it; ++it) {
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait_warp(&full_bar[s], ph);
                 tc_fence_after();
                 const int ntaps = p.groups[g_begin + it / kchunks].ntaps;
                 const uint32_t a_addr = smem_base + s * STAGE_BYTES;
@@ -330,7 +330,9 @@ static int launch_k(const CUtensorMap& mx, const CUtensorMap& mw, Params& p, lon
     // a grid of several waves: two CTAs per SM (one's epilogue under the other's mainloop) when two 2-stage rings fit
     const long ctas = tiles * (p.Cout / BN) * p.n_phase;
     constexpr int half_smem = (MAX_SMEM - 2048) / 2;
-    if (ctas > 2 * 148 && 2 * stage_bytes + 1024 <= half_smem) stages = (half_smem - 1024) / stage_bytes;
+    // ... never for CTA pairs: two pairs resident on the same two SMs would interleave their cta_group::2 TMEM allocations
+    // (each needs the allocation permit of BOTH SMs), and a pair kernel keeps the whole shared memory for its ring anyway
+    if (!PAIR && ctas > 2 * 148 && 2 * stage_bytes + 1024 <= half_smem) stages = (half_smem - 1024) / stage_bytes;
     if (stages < 2) return AGR_ERR_INVALID_ARGUMENT;
     p.stages = stages;
     const int smem = stages * stage_bytes + 1024;
@@ -427,7 +429,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (int g = p.gbegin[phase]; g < p.gbegin[phase + 1]; ++g) {
                 const int x0 = p.in_stride * w0 + p.groups[g].dx, y0 = p.in_stride * h0 + p.groups[g].dy;
                 for (int ck = 0; ck < kchunks; ++ck) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_wait_warp(&empty_bar[s], ph ^ 1);
                     mbar_expect_tx_p(&full_bar[s], (uint32_t)a_bytes, el);
                     tma_load_4d_p(a_base + (uint32_t)(s * A_SLOT), &map_x, smem_u32(&full_bar[s]), ck * BK, x0, y0, img, el);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -438,7 +440,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         // ================= MMA issuer: convergent loop, predicated issue =================
         const uint32_t el = elect_one();
         const uint32_t idesc = umma_idesc2(BM, BN, 0, B_MN ? 1 : 0);
-        mbar_wait(&w_bar, 0);
+        mbar_wait_warp(&w_bar, 0);
         tc_fence_after();
         const uint32_t w_addr = smem_u32(w_smem), a_base = smem_u32(a_ring);
         int s = 0; uint32_t ph = 0;
@@ -446,14 +448,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tl) {
             const int phase = tile % p.n_phase;
             const int buf = tl & 1;
-            mbar_wait(&tempty_bar[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));     // the epilogue has drained this accumulator
+            mbar_wait_warp(&tempty_bar[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));     // the epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
             uint32_t acc = 0;
             for (int g = p.gbegin[phase]; g < p.gbegin[phase + 1]; ++g) {
                 const TapGroup grp = p.groups[g];
                 for (int ck = 0; ck < kchunks; ++ck) {
-                    mbar_wait(&full_bar[s], ph);
+                    mbar_wait_warp(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t a_addr = a_base + (uint32_t)(s * A_SLOT);
                     for (int t = 0; t < grp.ntaps; ++t) {
@@ -481,7 +483,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const int img = rest / tiles_img, tile_m = rest - img * tiles_img;
             const int h0 = (tile_m / tiles_w) * TILE_H, w0 = (tile_m % tiles_w) * TILE_W;
             const int buf = tl & 1;
-            mbar_wait(&tfull_bar[buf], (uint32_t)((tl >> 1) & 1));
+            mbar_wait_warp(&tfull_bar[buf], (uint32_t)((tl >> 1) & 1));
             tc_fence_after();
             const int oy = (h0 + row / TILE_W) * p.out_stride + p.py[phase];
             const int ox = (w0 + row % TILE_W) * p.out_stride + p.px[phase];
@@ -543,9 +545,11 @@ int conv_tc_generation() {
     return g_generation;
 }
 
-// The persistent 64-channel kernel (AGR_CONV_PERSISTENT=0 switches it off) is used for single-phase geometries only: with the
-// warp-uniform issue loop it measured 0.55 vs 0.60 ms on the 16 x 512^2 64 -> 64 layer, but 0.62 vs 0.52 ms on the transposed
-// 128 -> 64 layer, whose four output phases have 1-4 taps each (profiles/r02_conv_generations_b.txt).
+// The persistent 64-channel kernel (AGR_CONV_PERSISTENT=0 switches it off) serves single-phase geometries only: 0.55 vs 0.60 ms
+// on the 16 x 512^2 64 -> 64 layer, 40.85 vs 41.3 ms per train step; the transposed 128 -> 64 layer (four output phases of 1-4
+// taps) is faster on one tile per CTA (0.52 vs 0.62 ms).  History: with independent per-lane mbarrier polling this kernel hung
+// the captured step in 3 of 5 runs (a lane lagging a full ring cycle sees its parity again); with the lockstep wait
+// (conv_common.cuh mbar_wait_warp) 0 of 6 — profiles/r02_hang_hunt.txt.
 static int g_persistent = -1;
 
 // Persistent kernel: Cout = 64, the whole weight fits next to a >= 3-deep box ring, and there are several waves of tiles.

@@ -96,7 +96,7 @@ class ProductWorkload:
         # the screen), so the workload would not be stationary.  The Adam arithmetic does not depend on lr.
         self.opt = optim.FlatAdam(self.net.parameters(), lr=lr)
         # owner-computes (parallel.py): a rank holds no gradient for the networks it does not run; the all-reduce brings it
-        self.opt.assume_all_active = world > 1 and self.net.net_parallel
+        self.opt.assume_all_active = bool(self.net.net_parallel)
         extrs, Ks = S.ring_cameras(n_views, img=IMG)
         self.views = list(range(rank, n_views, world))
         self.extrs, self.Ks = [extrs[v] for v in self.views], [Ks[v] for v in self.views]
@@ -615,7 +615,7 @@ def main():
                                "depth term, offset regulariser), synthetic %dk-Gaussian capsule avatar, 1 pose x %d views @1024x1024, "
                                "%s StyleUNet, view-sharded over %d GPU(s)" % (args.config - 1, wl.P // 1000, n_views, args.dtype, world),
                    "gaussians": wl.P, "views_per_step": n_views, "views_per_rank": len(wl.views), "image": [IMG, IMG],
-                   "parallelism": ("view-shard x%d + 1 all-reduce" % world) + (", per-pose networks on owner ranks (broadcast / reduce of their outputs)" if (world > 1 and wl.net.net_parallel) else ""), "cuda_graph": not args.no_graph,
+                   "parallelism": ("view-shard x%d + 1 all-reduce" % world) + (", per-pose networks on owner ranks (broadcast / reduce of their outputs)" if wl.net.net_parallel else ""), "cuda_graph": not args.no_graph,
                    "tile_instances_per_step": instances,
                    "l2": "step working set (activations, maps, instance streams: several GB) exceeds the 126 MB L2; no explicit flush",
                    "library_ops": list(__import__("animatablegaussians_b200.styleunet_ops", fromlist=["x"]).LIBRARY_OPS)},
