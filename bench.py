@@ -316,9 +316,10 @@ def run_check(args, rank, world, device):
                             # Adam's first step is -lr * g / (|g| + eps): entries with |g| ~ eps amplify rounding; compare
                             # where the 1-GPU gradient is clearly non-zero
                             "delta_rel_l2": rel(delta[::stride].cpu()[ref["grad"].abs() > 1e-6], ref["delta"][ref["grad"].abs() > 1e-6])}
-            # tolerances: fp32 summation order (atomics in the blend backward, the all-reduce tree) and, through it, a few
-            # leaky-ReLU kink / alpha-threshold flips per million gradient entries
-            res["vs_n1"]["ok"] = bool(res["vs_n1"]["loss_rel"] < 1e-5 and res["vs_n1"]["grad_rel_l2"] < 2e-3 and res["vs_n1"]["delta_rel_l2"] < 2e-2)
+            # tolerances: fp32 summation order (atomics in the blend backward and in the loss sums — the loss of a rank is a
+            # float accumulated by thousands of block-level atomic adds: ~1e-5 relative —, the all-reduce tree) and, through
+            # it, a few leaky-ReLU kink / alpha-threshold flips per million gradient entries
+            res["vs_n1"]["ok"] = bool(res["vs_n1"]["loss_rel"] < 1e-4 and res["vs_n1"]["grad_rel_l2"] < 2e-3 and res["vs_n1"]["delta_rel_l2"] < 2e-2)
         print(json.dumps({"check": res}))
         sys.stdout.flush()
     if world > 1:
@@ -569,6 +570,8 @@ def main():
     # replay and would perturb the timed region anyway)
     graph, wl.graph = wl.graph, None
     wl.net.concurrent_nets = False   # one stream: the stage event pairs must not overlap each other
+    for sub in (wl.net.color_net, wl.net.position_net, wl.net.other_net):
+        sub.concurrent_decoders = False
     wl.step(False)
     stats.reset()
 
