@@ -57,7 +57,7 @@ class _OwnerBroadcast(torch.autograd.Function):
         else:
             flat = torch.empty(sum(sizes), dtype=dtype, device=dummy.device)
         dist.broadcast(flat, src=owner)
-        ctx.owner, ctx.metas, ctx.sizes, ctx.is_owner, ctx.dtype = owner, metas, sizes, rank == owner, dtype
+        ctx.owner, ctx.metas, ctx.sizes, ctx.is_owner, ctx.dtype, ctx.device = owner, metas, sizes, rank == owner, dtype, flat.device
         outs, o = [], 0
         for m, n in zip(metas, sizes):
             outs.append(_unflatten(flat[o:o + n], m))
@@ -68,7 +68,7 @@ class _OwnerBroadcast(torch.autograd.Function):
     def backward(ctx, *grads):
         parts = []
         for g, m, n in zip(grads, ctx.metas, ctx.sizes):
-            parts.append(torch.zeros(n, dtype=ctx.dtype, device=grads[0].device if grads[0] is not None else None) if g is None
+            parts.append(torch.zeros(n, dtype=ctx.dtype, device=ctx.device) if g is None
                          else _flatten(g.to(ctx.dtype) if m[1] is False else g.to(ctx.dtype).contiguous(memory_format=torch.channels_last)))
         flat = torch.cat(parts) if len(parts) > 1 else parts[0].clone()
         dist.reduce(flat, dst=ctx.owner, op=dist.ReduceOp.SUM)

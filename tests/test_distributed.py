@@ -101,9 +101,9 @@ def _owner_worker(rank, world, port, ret):
     w = torch.randn(5, 3, requires_grad=True)                         # the owner's "network"
     x4 = torch.randn(1, 4, 3, 2).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     dummy = torch.zeros(1, requires_grad=True)
-    tensors = [w * 2.0, x4 * 1.0] if rank == owner else []
+    tensors = [w * 2.0, x4 * 1.0, w * 3.0] if rank == owner else []
     metas, dtype = parallel.share_meta(owner, tensors)
-    a, b = parallel.owner_broadcast(owner, metas, dtype, dummy, tensors)
+    a, b, _unused = parallel.owner_broadcast(owner, metas, dtype, dummy, tensors)      # the third output receives no gradient
     # every rank uses the outputs with its own (rank-dependent) weights, like each rank rendering its own views
     loss = (a * (rank + 1.0)).sum() + (b * b * (rank + 2.0)).sum()
     loss.backward()
