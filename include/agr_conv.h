@@ -52,7 +52,8 @@ typedef struct AgrConvEpilogue {
     const float* noise_w;   /* (1) fp32 */
     const float* residual;  /* (OH,OW,Cout) fp32 shared by the N images: the view-independent half of a split contraction
                                (path 1 only) */
-    int32_t activate;       /* 0 none | 1 leaky-ReLU(0.2)*sqrt(2) (FusedLeakyReLU, fused_act.py:117-132) | 2 leaky-ReLU(0.2) */
+    int32_t activate;       /* 0 none | 1 leaky-ReLU(0.2)*sqrt(2) (FusedLeakyReLU, fused_act.py:117-132) | 2 leaky-ReLU(0.2) |
+                               3 ReLU (the VGG-16 trunk of LPIPS, network/lpips/pretrained_networks.py:96-134) */
     int32_t out_fp32;       /* != 0: store the raw fp32 accumulator in y (no bias / noise / activation; path 1 only) */
     int32_t w_cin_total;    /* weight holds w_cin_total >= Cin input channels per tap; 0 means Cin */
     int32_t w_cin_offset;   /* first input channel of the slice this call contracts with (multiple of 64 on path 1) */

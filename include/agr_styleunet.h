@@ -38,13 +38,13 @@ int agr_upfirdn2d(int32_t dtype, const void* x, void* y, int32_t N, int32_t H, i
 int agr_haar(int32_t dtype, int32_t mode, const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
              void* cuda_stream);
 
-/* y = act(x + noise_w[0] * noise[h][w] + bias[c]),  act = identity (activate 0) | lrelu(.,0.2)*sqrt(2) (1) | lrelu(.,0.2) (2).
+/* y = act(x + noise_w[0] * noise[h][w] + bias[c]),  act = identity (activate 0) | lrelu(.,0.2)*sqrt(2) (1) | lrelu(.,0.2) (2) | relu (3).
  * noise: (H,W) fp32 or NULL, indexed with pixel % noise_period (= H*W: one noise image shared by the batch);
  * noise_w: 1 fp32 on device or NULL; bias: (C) fp32 or NULL. */
 int agr_bias_act_forward(int32_t dtype, const void* x, void* y, int64_t pixels, int32_t C, const float* bias,
                          const float* noise, const float* noise_w, int64_t noise_period, int32_t activate,
                          void* cuda_stream);
-/* dx = dy * (activate ? (y > 0 ? gain : 0.2*gain) : 1), gain = sqrt2 (activate 1) or 1 (activate 2); d_bias[c] += sum dx; d_noise_w[0] += sum dx*noise.
+/* dx = dy * (activate ? (y > 0 ? gain : slope*gain) : 1), gain = sqrt2 (activate 1) or 1 (2, 3), slope = 0.2 (1, 2) or 0 (3); d_bias[c] += sum dx; d_noise_w[0] += sum dx*noise.
  * d_bias / d_noise_w (fp32) are ACCUMULATED into (caller zeroes); either may be NULL. y is the forward OUTPUT.
  * dx may be NULL when activate == 0 (dx == dy: only the reductions are computed). */
 int agr_bias_act_backward(int32_t dtype, const void* dy, const void* y, void* dx, int64_t pixels, int32_t C,
