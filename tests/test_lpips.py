@@ -72,3 +72,21 @@ def test_lpips_matches_reference(dtype, H, W, N, built_lib):
         assert float((x - y).abs().max() / val_ref.abs().max()) < 3 * tol_v
     rel = float((b.grad - a.grad).norm() / a.grad.norm())
     assert rel < tol_g, rel
+
+
+def test_head_formulas_match_reference_autograd():
+    """CPU: the closed-form forward / backward of the LPIPS head as the CUDA kernel computes it (oracle/lpips_oracle.py) against
+    autograd of the reference's own `normalize_tensor` + squared difference + lin weights + spatial mean, in float64."""
+    from oracle import lpips_oracle as lo
+    ref = _reference_lpips()
+    import network.lpips as ref_pkg
+    g = torch.Generator().manual_seed(9)
+    for C, H, W in ((64, 9, 7), (512, 4, 4)):
+        f = torch.relu(torch.randn(2, C, H, W, generator=g, dtype=torch.float64)).requires_grad_(True)
+        w = torch.rand(C, generator=g, dtype=torch.float64)
+        d = (ref_pkg.normalize_tensor(f[0:1]) - ref_pkg.normalize_tensor(f[1:2])) ** 2
+        val = (d * w[None, :, None, None]).sum(1, keepdim=True).mean([2, 3]).sum()
+        val.backward()
+        assert abs(float(lo.layer_forward(f.detach(), w)) - float(val)) < 1e-12
+        got = lo.layer_backward(f.detach(), w, 1.0)
+        assert torch.allclose(got, f.grad, rtol=1e-9, atol=1e-14)
