@@ -475,3 +475,23 @@ def test_grouped_equal_linear_equals_per_layer(built_lib):
         if gb is not None:
             assert torch.equal(gb, m.bias.grad)
     _cmp(lat.grad, lat2.grad, 1e-5)
+
+
+def test_tail_state_exchange_bookkeeping():
+    """CPU: the tensors a rank receives from the prefix owner (parallel.py) are exactly what forward_view_tail() reads — both
+    decoders' (out, skip) and the skip feature of the tail level — and with_tail_state() puts them back where _decode looks."""
+    from animatablegaussians_b200 import styleunet
+    net = styleunet.DualStyleUNet(inp_size=512, inp_ch=3, out_ch=3, out_size=1024, style_dim=512, n_mlp=2)
+    n_cond = 1 + len(net.from_rgbs)
+    assert net._tail_cond_index() == [-n_cond]          # view_level 8 -> tail = decoder level 5 -> the finest encoder feature
+    mk = lambda tag: torch.full((1,), float(tag))
+    prefix = dict(latent=None, noise=None, plan=None, cond_list=[mk(10 + i) for i in range(n_cond)], s1=(mk(1), mk(2)), s2=(mk(3), mk(4)))
+    state = net.tail_state(prefix)
+    assert [float(t) for t in state] == [1, 2, 3, 4, 10]
+    received = [t + 100 for t in state]
+    empty = dict(latent=None, noise=None, plan=None, cond_list=[None] * n_cond, s1=None, s2=None)     # what tail_prefix() provides
+    got = net.with_tail_state(empty, received)
+    assert float(got["s1"][0]) == 101 and float(got["s1"][1]) == 102 and float(got["s2"][0]) == 103 and float(got["s2"][1]) == 104
+    assert float(got["cond_list"][-n_cond]) == 110 and all(c is None for c in got["cond_list"][1:])
+    # the level the tail starts at is the one _decode enters with start = view_level + 2
+    assert (net.view_level + 2) // 2 == len(net.to_rgbs1) - 1
