@@ -79,7 +79,7 @@ def roofline_tensor(st, steps, peaks):
     ms, n = st["stages"].get("styleunet_conv_tc", (0.0, 0))
     fl = st.get("work", {}).get("styleunet_conv_tc", 0.0)
     ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-    return {"bound": "tensor", "kernel": "conv_tc_kernel<BN,STAGES> + conv_wgrad_tc_kernel<MT,NT> (tcgen05.mma implicit-GEMM convolutions: forward, data gradient and weight gradient launches of every layer with Cin, Cout multiples of 64)",
+    return {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel (CTA pairs) / conv_tc3_kernel (persistent) + conv_wgrad_tc_kernel (tcgen05.mma implicit-GEMM convolutions: forward, data gradient and weight gradient launches of every layer with Cin, Cout multiples of 64)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": which,
             "launches_per_step": n / max(steps, 1), "algorithmic_flop_per_step": fl / max(steps, 1), "seconds_per_step": ms * 1e-3 / max(steps, 1)}
 
